@@ -1,0 +1,290 @@
+/*
+ * sliced_b200.h — C ABI of libsliced_b200.so, the B200 (sm_100a) implementation of the
+ * forward + backward op set of elftausend/sliced.
+ *
+ * This is the drop-in boundary: every entry point below is what a Rust `sliced-b200-sys`
+ * FFI crate binds so that sliced's own op traits (src/ops2/<op>/mod.rs, grad.rs) can be
+ * implemented `for CUDA<Mods>` in a new `src/ops2/<op>/cuda.rs` next to `cpu.rs` /
+ * `opencl.rs` (hook: reference src/lib.rs:24-25).  Each function cites the reference
+ * interface it replaces as `ref: file:line` (paths relative to the reference crate root).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  All matrix arguments are row-major,
+ *    contiguous device pointers (the reference has no strides / leading dimensions).
+ *  - Every function returns an sl_status (0 = ok, negative = error); nothing throws or
+ *    aborts across the boundary.  sl_last_error_string(ctx) describes the last failure.
+ *  - A sl_ctx owns one CUDA device + one stream.  All op calls are asynchronous on that
+ *    stream and ordered; only sl_read / sl_sync / scalar *_host calls block.
+ *  - "SET" entry points fully overwrite their output; "ACC" entry points `+=` into it,
+ *    exactly as the reference CPU slice function they replace does.
+ *  - dtype is one of sl_dtype.  f32 is supported everywhere; f64 and i32 are supported by
+ *    the element-wise / broadcast / reduction / transpose families and by the CUDA-core
+ *    gemm (the reference's unit tests are written in i32 / f64).  Unsupported
+ *    combinations return SL_ERR_UNSUPPORTED — there is no CPU fallback on this path.
+ */
+#ifndef SLICED_B200_H
+#define SLICED_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SL_ABI_VERSION 1
+
+typedef struct sl_ctx sl_ctx;
+
+typedef enum sl_status {
+    SL_OK = 0,
+    SL_ERR_INVALID_ARG = -1,
+    SL_ERR_CUDA = -2,
+    SL_ERR_UNSUPPORTED = -3,
+    SL_ERR_NCCL = -4,
+    SL_ERR_NO_DEVICE = -5
+} sl_status;
+
+typedef enum sl_dtype { SL_F32 = 0, SL_F64 = 1, SL_I32 = 2 } sl_dtype;
+
+/* Binary element-wise operators. ref: src/ops2/binary_ew/mod.rs:67-99 (add/mul/div/sub). */
+typedef enum sl_binop { SL_ADD = 0, SL_SUB = 1, SL_MUL = 2, SL_DIV = 3 } sl_binop;
+
+/*
+ * Unary functions reachable through custos `apply_fn` / `add_unary_grad` from sliced.
+ * Forward f(x) and the derivative g(x) used by the *_grad entry point (x_grad += g(x)*out_grad)
+ * are exactly the closures the reference registers:
+ *   SQUARE        f = x*x              g = x*2                       ref: src/ops.rs:36,40
+ *   POW(p0)       f = x^p0             g = x^(p0-1) * p0             ref: src/ops.rs:65,70-72
+ *   RELU          f = (x>=0)*x         g = (x>=0)                    ref: src/matrix.rs:181,186
+ *   TANH          f = tanh(x)          g = 1 - tanh(x)^2             ref: src/matrix.rs:218,223-225
+ *   SIGMOID       f = 1/(1+exp(-x))    g = exp(-x)/(1+exp(-x))^2     ref: src/matrix.rs:246-250,255-257
+ *   EXP           f = exp(x)           g = exp(x)                    ref: src/ops.rs:438 (grad: :403, commented)
+ *   LN            f = ln(x)            g = 1/x
+ *   NEG_LN        f = -ln(x)           g = -1/x                      ref: examples/nn.rs:137
+ *   CLIP(p0,p1)   f = min(max(x,p0),p1) g = (p0<=x && x<=p1)         ref: src/ops.rs:423
+ *   NEG           f = -x               g = -1
+ *   MUL_SCALAR    f = x*p0             g = p0
+ *   NEG_DIV_SCALAR f = (-x)/p0         g = -1/p0                     ref: examples/nn.rs:151
+ *   ADD_SCALAR    f = x+p0             g = 1
+ */
+typedef enum sl_unop {
+    SL_UN_SQUARE = 0,
+    SL_UN_POW = 1,
+    SL_UN_RELU = 2,
+    SL_UN_TANH = 3,
+    SL_UN_SIGMOID = 4,
+    SL_UN_EXP = 5,
+    SL_UN_LN = 6,
+    SL_UN_NEG_LN = 7,
+    SL_UN_CLIP = 8,
+    SL_UN_NEG = 9,
+    SL_UN_MUL_SCALAR = 10,
+    SL_UN_NEG_DIV_SCALAR = 11,
+    SL_UN_ADD_SCALAR = 12,
+    SL_UN_COUNT_
+} sl_unop;
+
+/* gemm arithmetic mode (f32 only; f64/i32 always use the CUDA-core kernel). */
+typedef enum sl_gemm_mode {
+    SL_GEMM_3XTF32 = 0, /* default: tcgen05 kind::tf32, 3 MMAs per k-slice (hi*hi + hi*lo + lo*hi), fp32-class accuracy */
+    SL_GEMM_TF32 = 1,   /* flagged fast mode: one tcgen05 kind::tf32 MMA per k-slice */
+    SL_GEMM_SIMT = 2    /* exact fp32 FMA accumulation on CUDA cores (any shape / dtype) */
+} sl_gemm_mode;
+
+/* ---------------------------------------------------------------- context / memory */
+
+int sl_abi_version(void);
+/* Number of visible CUDA devices (0 on a box without a GPU; never fails). */
+int sl_device_count(void);
+
+/* ref: custos `CUDA::<Mods>::new(idx)` † (device object; hook src/lib.rs:24-25). */
+int sl_ctx_create(int device, sl_ctx** out_ctx);
+/* Same, but borrows an existing cudaStream_t (e.g. torch's current stream) instead of creating one. */
+int sl_ctx_create_on_stream(int device, void* cuda_stream, sl_ctx** out_ctx);
+int sl_ctx_destroy(sl_ctx* ctx);
+const char* sl_last_error_string(sl_ctx* ctx);
+void* sl_ctx_stream(sl_ctx* ctx);
+int sl_ctx_device(sl_ctx* ctx);
+/* Default gemm mode used when an entry point is passed mode < 0. Also read from env SLICED_GEMM_MODE={3xtf32,tf32,simt}. */
+int sl_ctx_set_gemm_mode(sl_ctx* ctx, int mode);
+/* Number of kernels this library launched on ctx since creation (bench.py's gpu_launches). */
+uint64_t sl_ctx_launch_count(sl_ctx* ctx);
+
+/* ref: custos `Alloc<T>::alloc` / `OnDropBuffer` † */
+int sl_malloc(sl_ctx* ctx, size_t bytes, void** out_dptr);
+int sl_free(sl_ctx* ctx, void* dptr);
+/* pinned host staging memory (ref: custos `Buffer::from((&device, slice))` † host source) */
+int sl_host_alloc(sl_ctx* ctx, size_t bytes, void** out_hptr);
+int sl_host_free(sl_ctx* ctx, void* hptr);
+/* ref: custos `WriteBuf::write` † — host -> device, async on the ctx stream */
+int sl_write(sl_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+/* ref: custos `Read::read` † — device -> host, blocks until the data is on the host */
+int sl_read(sl_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+/* ref: custos `CloneBuf` / `WriteBuf::write_buf` † — device -> device */
+int sl_copy(sl_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+/* ref: custos `ClearBuf::clear` † / `Gradients::zero_grad` (examples/nn.rs:186-188) */
+int sl_clear(sl_ctx* ctx, void* dst_dev, size_t bytes);
+int sl_fill(sl_ctx* ctx, int dtype, void* dst_dev, double value, size_t n);
+int sl_sync(sl_ctx* ctx);
+
+/* ---------------------------------------------------------------- E: element-wise / broadcast */
+
+/* out[i] = lhs[i] op rhs[i]  (SET).  ref: src/ops2/binary_ew/mod.rs:55-100, cpu_stack.rs:42-54 */
+int sl_binary_ew(sl_ctx* ctx, int dtype, int binop, const void* lhs, const void* rhs, void* out, size_t n);
+/* lhs_grad[i] += dl(l,r)*og[i]; rhs_grad[i] += dr(l,r)*og[i]  (ACC; either grad may be NULL).
+ * (dl,dr): ADD (1,1) SUB (1,-1) MUL (r,l) DIV (1/r, l/-(r*r)).
+ * ref: src/ops2/binary_ew/grad.rs:22-36, grad/cpu_stack.rs:40-60; closures src/ops.rs:125-126,144-145,163-164 */
+int sl_binary_ew_grad(sl_ctx* ctx, int dtype, int binop, const void* lhs, const void* rhs,
+                      void* lhs_grad, void* rhs_grad, const void* out_grad, size_t n);
+/* lhs_grad += og; rhs_grad += og.  ref: src/ops2/binary_ew/grad.rs:38-45, grad/cpu_stack.rs:80-88 */
+int sl_add_ew_grad(sl_ctx* ctx, int dtype, void* lhs_grad, void* rhs_grad, const void* out_grad, size_t n);
+
+/* out[i] = f(x[i]) (SET).  ref: custos `ApplyFunction::apply_fn` † as called from src/ops.rs:36,65,423,438, src/matrix.rs:181,218,246 */
+int sl_unary(sl_ctx* ctx, int dtype, int unop, double p0, double p1, const void* x, void* out, size_t n);
+/* x_grad[i] += g(x[i]) * out_grad[i] (ACC).  ref: custos `UnaryGrad::add_unary_grad` † as called from src/ops.rs:38-41,67-73, src/matrix.rs:183-188 */
+int sl_unary_grad(sl_ctx* ctx, int dtype, int unop, double p0, double p1, const void* x, void* x_grad,
+                  const void* out_grad, size_t n);
+
+/* out[r,c] = lhs[r,c] op rhs[c] (SET, new buffer).  ref: src/ops2/row_op/mod.rs:17-38, cpu.rs:44-65,81-90 */
+int sl_row_op(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, const void* lhs, const void* rhs, void* out);
+/* = sl_row_op(ADD).  ref: src/ops2/row_op/mod.rs:28-38 */
+int sl_add_row(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* lhs, const void* rhs, void* out);
+/* lhs[r,c] += rhs[c] in place.  ref: src/ops2/row_op/mod.rs:40-46, cpu.rs:15-30,67-79 */
+int sl_add_row_mut(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* lhs, const void* rhs);
+/* lhs_grad = out_grad (SET copy); rhs_grad[c] += sum_r out_grad[r,c] (ACC).  ref: src/ops2/row_op/grad.rs:25-32, grad/cpu.rs:54-64 */
+int sl_add_row_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* lhs_grad, void* rhs_grad, const void* out_grad);
+/* rhs_grad[c] += sum_r out_grad[r,c] (ACC).  ref: src/ops2/row_op/grad.rs:34-40, grad/cpu.rs:42-50 */
+int sl_add_row_mut_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* rhs_grad, const void* out_grad);
+/* lhs_grad[r,c] += dl(rhs[c])*og[r,c]; rhs_grad[c] += sum_r dr(lhs[r,c])*og[r,c] (ACC), with
+ * (dl,dr) = ADD (1,1), SUB (1,-1), MUL (v,v).  ref: src/ops2/row_op/grad.rs:13-23, grad/cpu.rs:66-88 */
+int sl_row_op_grad(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, const void* lhs, const void* rhs,
+                   void* lhs_grad, void* rhs_grad, const void* out_grad);
+
+/* out[r,c] = lhs[r,c] op rhs[r] (SET).  ref: src/ops2/col_op/mod.rs:20-58 (sub_cols, div_cols), cpu.rs:40-50 */
+int sl_col_op(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, const void* lhs, const void* rhs, void* out);
+/* lhs_grad[r,c] += dl(l,rhs[r])*og; rhs_grad[r] += sum_c dr(l,rhs[r])*og (ACC), (dl,dr) as sl_binary_ew_grad.
+ * ref: src/ops2/col_op/grad/cpu.rs:37-89 */
+int sl_col_op_grad(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, const void* lhs, const void* rhs,
+                   void* lhs_grad, void* rhs_grad, const void* out_grad);
+
+/* w[i] -= g[i]*lr.  ref: examples/nn.rs:108-119 (SGD::step), examples/sine_net.rs:105-116 */
+int sl_sgd_step(sl_ctx* ctx, int dtype, void* w, const void* g, double lr, size_t n);
+
+/* The 5-op chained graph of examples/chained_perf.rs:86-90 in one pass:
+ *   out = (x*x)*x + (b+x)*b        (SET; same operation order as the reference's 5 separate passes) */
+int sl_chained_fwd(sl_ctx* ctx, int dtype, const void* x, const void* b, void* out, size_t n);
+/* ... and its tape (reverse order of the 5 grad closures) in one pass:
+ *   x_grad += d out/d x * og ; b_grad += d out/d b * og   (ACC) */
+int sl_chained_bwd(sl_ctx* ctx, int dtype, const void* x, const void* b, void* x_grad, void* b_grad,
+                   const void* out_grad, size_t n);
+
+/* ---------------------------------------------------------------- G: gemm / trans_gemm */
+
+/* out[m x n] = lhs[m x k] * rhs[k x n]  (SET).  mode < 0 -> ctx default.
+ * ref: src/ops2/gemm/mod.rs:21-32, cpu_stack.rs:27-45 (BLAS call `T::gemm(m,n,k,..)` :39) */
+int sl_gemm(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, void* out, int mode);
+/* custos GenericBlas::gemmT(m,n,k,a,b,c): c[m x n] = a[m x k] * b[n x k]^T (SET).
+ * ref: src/ops2/gemm/grad/cpu_stack.rs:36, tests/test_trans_gemm.rs:73-105 */
+int sl_gemm_nt(sl_ctx* ctx, int dtype, size_t m, size_t n, size_t k, const void* a, const void* b, void* c, int mode);
+/* custos GenericBlas::Tgemm(m,n,k,a,b,c): c[m x n] = a[k x m]^T * b[k x n] (SET).
+ * ref: src/ops2/gemm/grad/cpu_stack.rs:39, tests/test_trans_gemm.rs:6-69 */
+int sl_gemm_tn(sl_ctx* ctx, int dtype, size_t m, size_t n, size_t k, const void* a, const void* b, void* c, int mode);
+/* General form: c[m x n] (=|+=) op(a) * op(b); trans_a: a is stored [k x m]; trans_b: b is stored [n x k]. */
+int sl_gemm_ex(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k,
+               const void* a, const void* b, void* c, int accumulate, int mode);
+/* lhs_grad[m x k] (=|+=) out_grad * rhs^T ; rhs_grad[k x n] (=|+=) lhs^T * out_grad.
+ * NULL grad pointer == `!requires_grad()`.  accumulate=0 reproduces the CPU reference (beta = 0),
+ * accumulate=1 the OpenCL reference (src/ops2/gemm/grad/opencl.rs:20,33).
+ * ref: src/ops2/gemm/grad.rs:14-29, grad/cpu_stack.rs:24-41 */
+int sl_gemm_grad(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs,
+                 void* lhs_grad, void* rhs_grad, const void* out_grad, int accumulate, int mode);
+
+/* ---------------------------------------------------------------- R: reductions */
+
+/* Scalar reductions; result is written to a device scalar `out_dev` (1 element of dtype).
+ * ref: src/ops2/sum/mod.rs:15-17 + cpu.rs:18-20; mean/mod.rs:15-17 + cpu.rs:34-36; max/mod.rs:16-18 + cpu.rs:11-13 */
+int sl_sum(sl_ctx* ctx, int dtype, const void* x, size_t n, void* out_dev);
+int sl_mean(sl_ctx* ctx, int dtype, const void* x, size_t n, void* out_dev);
+int sl_max(sl_ctx* ctx, int dtype, const void* x, size_t n, void* out_dev);
+
+/* "rows" ops reduce over rows (output length = cols); "cols" ops reduce over columns (output length = rows).
+ * All SET: the output is fully overwritten (the reference's sum_rows accumulates into a fresh zeroed buffer).
+ * ref: sum_rows src/ops2/sum/cpu.rs:33-41,78-84; sum_cols :54-63,86-90;
+ *      mean_rows src/ops2/mean/cpu.rs:16-20,38-43; mean_cols :27-31,45-49;
+ *      max_rows src/ops2/max/cpu.rs:37-54; max_cols :64-80.
+ * max_*: idx_out (int32, may be NULL) receives the FIRST index attaining the maximum. */
+int sl_sum_rows(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out);
+int sl_sum_cols(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out);
+int sl_mean_rows(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out);
+int sl_mean_cols(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out);
+int sl_max_rows(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out, int32_t* idx_out);
+int sl_max_cols(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out, int32_t* idx_out);
+
+/* Gradients (all ACC into x_grad).
+ * sum_rows_grad:  xg[r,c] += og[c]             ref: src/ops2/sum/grad/cpu.rs:41-48
+ * sum_cols_grad:  xg[r,c] += og[r]             ref: src/ops2/sum/grad/cpu.rs:50-56
+ * mean_rows_grad: xg[r,c] += (T(cols)/T(len))*og[c]   ref: src/ops2/mean/grad/cpu.rs:30-47
+ * mean_cols_grad: xg[r,c] += og[r]/T(cols)     ref: src/ops2/mean/grad/cpu.rs:56-63
+ * max_rows_grad:  every (r,c) with x[r,c]==out[c] gets += og[c]   ref: src/ops2/max/grad/cpu.rs:40-55
+ * max_cols_grad:  the FIRST c with x[r,c]==out[r] gets += og[r]   ref: src/ops2/max/grad/cpu.rs:57-69 */
+int sl_sum_rows_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_grad, const void* out_grad);
+int sl_sum_cols_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_grad, const void* out_grad);
+int sl_mean_rows_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_grad, const void* out_grad);
+int sl_mean_cols_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_grad, const void* out_grad);
+int sl_max_rows_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* out, const void* x, void* x_grad,
+                     const void* out_grad);
+int sl_max_cols_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* out, const void* x, void* x_grad,
+                     const void* out_grad);
+/* Same result as sl_max_cols_grad, using the argmax saved by sl_max_cols (8 B per row instead of a scan). */
+int sl_max_cols_grad_idx(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const int32_t* idx, void* x_grad,
+                         const void* out_grad);
+
+/* ---------------------------------------------------------------- T: transpose */
+
+/* out[c*rows + r] (=|+=) x[r*cols + c].  accumulate=0: SET.
+ * ref: src/ops2/transpose/mod.rs:17-21, cpu.rs:10-26,41-52; grad: transpose/grad.rs:13-26, grad/cpu.rs:17-25
+ * (the CPU reference's grad is effectively SET — stray `b[idx] = row.clone()` at transpose/cpu.rs:23 —
+ *  the OpenCL reference's is ACC; both are available through `accumulate`). */
+int sl_transpose(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out, int accumulate);
+
+/* ---------------------------------------------------------------- S: softmax */
+
+/* out[r,:] = exp(x[r,:] - max_c x[r,c]) / sum_c exp(..)  (SET; f32/f64).
+ * ref: src/ops2/softmax/mod.rs:16-18, cpu.rs:11-16 */
+int sl_softmax(sl_ctx* ctx, int dtype, size_t samples, size_t features, const void* x, void* out);
+/* x_grad[r,:] = (diag(s) - s s^T) g  ==  s * (g - <s,g>)   (SET; f32/f64).
+ * ref: src/ops2/softmax/grad.rs:15-24, grad/cpu.rs:14-62 */
+int sl_softmax_grad(sl_ctx* ctx, int dtype, size_t samples, size_t features, void* x_grad, const void* out,
+                    const void* out_grad);
+
+/* ---------------------------------------------------------------- next-row ops */
+
+/* out[i*n + i] = x[i] (only the diagonal is written).  ref: src/ops2/diagflat/cpu.rs:42-46 */
+int sl_diagflat(sl_ctx* ctx, int dtype, size_t n, const void* x, void* out);
+/* x_grad[i] += out_grad[i*n + i].  ref: src/ops2/diagflat/grad/cpu.rs:32-36 */
+int sl_diagflat_grad(sl_ctx* ctx, int dtype, size_t n, void* x_grad, const void* out_grad);
+/* out[i*highest_class + (size_t)classes[i]] = 1 (only the ones are written).  ref: src/ops2/onehot/cpu.rs:40-44 */
+int sl_onehot(sl_ctx* ctx, int dtype, size_t n, size_t highest_class, const void* classes, void* out);
+/* classes_grad[i] += out_grad[i*highest_class + classes[i]].  ref: src/ops2/onehot/grad/cpu.rs:3-12 */
+int sl_onehot_grad(sl_ctx* ctx, int dtype, size_t n, size_t highest_class, const void* classes, void* classes_grad,
+                   const void* out_grad);
+/* Per-row argmax of preds[rows x cols] compared with int32 labels -> number of matches in *count_dev (int32 device scalar).
+ * ref: examples/nn.rs:195-211 (host loop in the reference). */
+int sl_count_correct(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* preds, const int32_t* labels,
+                     int32_t* count_dev);
+
+/* ---------------------------------------------------------------- DP: data-parallel exchange (new) */
+
+#define SL_COMM_ID_BYTES 128
+/* Fills a 128-byte opaque id on ONE rank; the caller ships it to the other ranks (e.g. torch.distributed broadcast). */
+int sl_comm_unique_id(void* id_out_128);
+int sl_comm_init_rank(sl_ctx* ctx, int nranks, int rank, const void* id_128);
+/* In-place sum all-reduce of a device buffer across the ranks of the communicator (NCCL over NVLink). */
+int sl_allreduce_sum(sl_ctx* ctx, int dtype, void* buf, size_t n);
+int sl_comm_destroy(sl_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLICED_B200_H */
