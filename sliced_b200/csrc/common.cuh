@@ -1,0 +1,123 @@
+// common.cuh — shared plumbing of libsliced_b200.so: context object, error handling, dtype dispatch,
+// 128-bit streaming load/store helpers.  B200 / sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <type_traits>
+
+#include "../../include/sliced_b200.h"
+
+struct sl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int num_sms = 148;
+    int gemm_mode = SL_GEMM_3XTF32;
+    uint64_t launches = 0;
+    std::string last_error;
+    // grow-only scratch (reduction partials, gemm operand planes); owned by the ctx, never user visible
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    void* ws2 = nullptr;  // second scratch region (gemm planes live here so reductions can run concurrently in-order)
+    size_t ws2_bytes = 0;
+    // NCCL (dlopen'ed lazily)
+    void* nccl_comm = nullptr;
+    int nranks = 1;
+    int rank = 0;
+};
+
+int sl_set_error(sl_ctx* ctx, int code, const char* fmt, ...);
+int sl_ws_reserve(sl_ctx* ctx, size_t bytes, void** out);
+int sl_ws2_reserve(sl_ctx* ctx, size_t bytes, void** out);
+
+#define SL_REQUIRE(ctx, cond, msg)                                                   \
+    do {                                                                             \
+        if (!(cond)) return sl_set_error((ctx), SL_ERR_INVALID_ARG, "%s: %s", __func__, (msg)); \
+    } while (0)
+
+#define SL_CUDA(ctx, expr)                                                                           \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return sl_set_error((ctx), SL_ERR_CUDA, "%s: %s -> %s", __func__, #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+// Launch + count + check.  Every kernel this library runs goes through here (sl_ctx_launch_count).
+#define SL_LAUNCH(ctx, kernel, grid, block, smem, ...)                                               \
+    do {                                                                                             \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                             \
+        (ctx)->launches++;                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                        \
+        if (e__ != cudaSuccess)                                                                      \
+            return sl_set_error((ctx), SL_ERR_CUDA, "%s: launch %s -> %s", __func__, #kernel, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define SL_DISPATCH_DTYPE(ctx, dtype, T, ...)                                         \
+    switch (dtype) {                                                                  \
+    case SL_F32: { using T = float; __VA_ARGS__; } break;                             \
+    case SL_F64: { using T = double; __VA_ARGS__; } break;                            \
+    case SL_I32: { using T = int32_t; __VA_ARGS__; } break;                           \
+    default: return sl_set_error((ctx), SL_ERR_INVALID_ARG, "%s: bad dtype %d", __func__, (int)(dtype)); \
+    }
+
+#define SL_DISPATCH_FLOAT(ctx, dtype, T, ...)                                         \
+    switch (dtype) {                                                                  \
+    case SL_F32: { using T = float; __VA_ARGS__; } break;                             \
+    case SL_F64: { using T = double; __VA_ARGS__; } break;                            \
+    default: return sl_set_error((ctx), SL_ERR_UNSUPPORTED, "%s: dtype %d unsupported (f32/f64 only)", __func__, (int)(dtype)); \
+    }
+
+static inline size_t sl_dtype_size(int dtype) { return dtype == SL_F64 ? 8 : 4; }
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit packs.  VEC = 16 / sizeof(T) elements travel in one LDG.128 / STG.128.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct alignas(16) Pack {
+    static constexpr int N = 16 / sizeof(T);
+    T v[N];
+};
+
+// streaming (read-once) 128-bit load: bypass L1 allocation, read-only path
+template <typename T>
+__device__ __forceinline__ Pack<T> ld_stream(const T* p) {
+    Pack<T> r;
+    uint32_t a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+    uint4 u = make_uint4(a, b, c, d);
+    r = *reinterpret_cast<Pack<T>*>(&u);
+    return r;
+}
+// plain 128-bit load (for buffers that are read-modify-written in the same kernel)
+template <typename T>
+__device__ __forceinline__ Pack<T> ld_pack(const T* p) {
+    return *reinterpret_cast<const Pack<T>*>(p);
+}
+template <typename T>
+__device__ __forceinline__ void st_pack(T* p, const Pack<T>& v) {
+    *reinterpret_cast<Pack<T>*>(p) = v;
+}
+// streaming store: written once, not re-read by this kernel
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, const Pack<T>& v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(&v);
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
+static inline bool sl_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+__device__ __forceinline__ T sl_max2(T a, T b) { return a > b ? a : b; }
+template <>
+__device__ __forceinline__ float sl_max2<float>(float a, float b) { return fmaxf(a, b); }
+template <>
+__device__ __forceinline__ double sl_max2<double>(double a, double b) { return fmax(a, b); }
+
+static inline unsigned sl_pow2_ceil(unsigned x) {
+    unsigned p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}

@@ -1,0 +1,193 @@
+// ctx.cu — context, memory and transfer entry points of the C ABI (include/sliced_b200.h).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local std::string g_noctx_error;
+
+int sl_set_error(sl_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    else g_noctx_error = buf;
+    return code;
+}
+
+static int grow(sl_ctx* ctx, void** p, size_t* cur, size_t bytes, void** out) {
+    if (bytes > *cur) {
+        // grow-only; in-flight kernels using the old block are ordered before the free on this stream
+        if (*p) {
+            SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            SL_CUDA(ctx, cudaFree(*p));
+            *p = nullptr;
+            *cur = 0;
+        }
+        size_t want = bytes + (bytes >> 3);
+        want = (want + 255) & ~size_t(255);
+        SL_CUDA(ctx, cudaMalloc(p, want));
+        *cur = want;
+    }
+    *out = *p;
+    return SL_OK;
+}
+
+int sl_ws_reserve(sl_ctx* ctx, size_t bytes, void** out) { return grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes, out); }
+int sl_ws2_reserve(sl_ctx* ctx, size_t bytes, void** out) { return grow(ctx, &ctx->ws2, &ctx->ws2_bytes, bytes, out); }
+
+extern "C" {
+
+int sl_abi_version(void) { return SL_ABI_VERSION; }
+
+int sl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int ctx_create_common(int device, void* stream, bool borrow, sl_ctx** out_ctx) {
+    if (!out_ctx) return sl_set_error(nullptr, SL_ERR_INVALID_ARG, "sl_ctx_create: out_ctx is NULL");
+    *out_ctx = nullptr;
+    int n = sl_device_count();
+    if (n <= 0) return sl_set_error(nullptr, SL_ERR_NO_DEVICE, "sl_ctx_create: no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return sl_set_error(nullptr, SL_ERR_INVALID_ARG, "sl_ctx_create: device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return sl_set_error(nullptr, SL_ERR_CUDA, "sl_ctx_create: cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return sl_set_error(nullptr, SL_ERR_UNSUPPORTED, "sl_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                            device, prop.major, prop.minor);
+    sl_ctx* ctx = new sl_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return sl_set_error(nullptr, SL_ERR_CUDA, "sl_ctx_create: cudaSetDevice(%d) failed", device);
+    }
+    if (borrow) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->owns_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return sl_set_error(nullptr, SL_ERR_CUDA, "sl_ctx_create: cudaStreamCreate failed");
+        }
+        ctx->owns_stream = true;
+    }
+    const char* env = getenv("SLICED_GEMM_MODE");
+    if (env) {
+        if (!strcmp(env, "tf32")) ctx->gemm_mode = SL_GEMM_TF32;
+        else if (!strcmp(env, "simt")) ctx->gemm_mode = SL_GEMM_SIMT;
+        else ctx->gemm_mode = SL_GEMM_3XTF32;
+    }
+    *out_ctx = ctx;
+    return SL_OK;
+}
+
+int sl_ctx_create(int device, sl_ctx** out_ctx) { return ctx_create_common(device, nullptr, false, out_ctx); }
+int sl_ctx_create_on_stream(int device, void* cuda_stream, sl_ctx** out_ctx) {
+    return ctx_create_common(device, cuda_stream, true, out_ctx);
+}
+
+int sl_comm_destroy(sl_ctx* ctx);
+
+int sl_ctx_destroy(sl_ctx* ctx) {
+    if (!ctx) return SL_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    sl_comm_destroy(ctx);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->ws2) cudaFree(ctx->ws2);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SL_OK;
+}
+
+const char* sl_last_error_string(sl_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_noctx_error.c_str(); }
+void* sl_ctx_stream(sl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int sl_ctx_device(sl_ctx* ctx) { return ctx ? ctx->device : -1; }
+uint64_t sl_ctx_launch_count(sl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sl_ctx_set_gemm_mode(sl_ctx* ctx, int mode) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    SL_REQUIRE(ctx, mode >= SL_GEMM_3XTF32 && mode <= SL_GEMM_SIMT, "bad mode");
+    ctx->gemm_mode = mode;
+    return SL_OK;
+}
+
+int sl_malloc(sl_ctx* ctx, size_t bytes, void** out_dptr) {
+    SL_REQUIRE(ctx, ctx && out_dptr, "NULL argument");
+    *out_dptr = nullptr;
+    if (bytes == 0) return SL_OK;
+    SL_CUDA(ctx, cudaSetDevice(ctx->device));
+    SL_CUDA(ctx, cudaMalloc(out_dptr, bytes));
+    return SL_OK;
+}
+
+int sl_free(sl_ctx* ctx, void* dptr) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (!dptr) return SL_OK;
+    SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SL_CUDA(ctx, cudaFree(dptr));
+    return SL_OK;
+}
+
+int sl_host_alloc(sl_ctx* ctx, size_t bytes, void** out_hptr) {
+    SL_REQUIRE(ctx, ctx && out_hptr, "NULL argument");
+    SL_CUDA(ctx, cudaHostAlloc(out_hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SL_OK;
+}
+
+int sl_host_free(sl_ctx* ctx, void* hptr) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (hptr) SL_CUDA(ctx, cudaFreeHost(hptr));
+    return SL_OK;
+}
+
+int sl_write(sl_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (bytes == 0) return SL_OK;
+    SL_REQUIRE(ctx, dst_dev && src_host, "NULL pointer");
+    SL_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SL_OK;
+}
+
+int sl_read(sl_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (bytes == 0) return SL_OK;
+    SL_REQUIRE(ctx, dst_host && src_dev, "NULL pointer");
+    SL_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SL_OK;
+}
+
+int sl_copy(sl_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (bytes == 0) return SL_OK;
+    SL_REQUIRE(ctx, dst_dev && src_dev, "NULL pointer");
+    SL_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return SL_OK;
+}
+
+int sl_clear(sl_ctx* ctx, void* dst_dev, size_t bytes) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (bytes == 0) return SL_OK;
+    SL_REQUIRE(ctx, dst_dev, "NULL pointer");
+    SL_CUDA(ctx, cudaMemsetAsync(dst_dev, 0, bytes, ctx->stream));
+    return SL_OK;
+}
+
+int sl_sync(sl_ctx* ctx) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SL_OK;
+}
+
+}  // extern "C"

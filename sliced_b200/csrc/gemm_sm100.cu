@@ -1,0 +1,648 @@
+// gemm_sm100.cu — family G: the dense contractions (gemm, gemmT, Tgemm and therefore gemm_grad) on the 5th-generation
+// tensor cores of B200: TMA -> 128B-swizzled shared memory -> tcgen05.mma kind::tf32 -> fp32 accumulators in TMEM ->
+// tcgen05.ld epilogue.  Hand-written PTX; no CUTLASS / cuBLAS on this path.
+//
+// Precision modes (sl_gemm_mode):
+//   SL_GEMM_3XTF32 (default)  every fp32 operand x is split into  hi = rna_tf32(x),  lo = rna_tf32(x - hi)  and each
+//                             k-slice issues three MMAs into the same TMEM accumulator:  lo*hi + hi*lo + hi*hi.
+//                             The dropped lo*lo term and the rounding of lo are both ~2^-24 relative, i.e. fp32-class.
+//   SL_GEMM_TF32              one MMA per k-slice on the raw fp32 bits (the tensor core reads the top 19 bits).
+//
+// tcgen05.mma takes both operands from shared memory through descriptors, so there is no register stage in which to
+// split an operand.  The split is therefore done by a bandwidth-bound "prep" pass that writes K-major hi / lo planes
+// into the context's scratch; the same pass transposes an operand whose contraction index is not contiguous
+// (gemm's rhs, Tgemm's lhs and rhs), so that the MMA kernel only ever sees K-major A[M x K] and B[N x K] tiles
+// (the canonical, swizzle-128B K-major UMMA layout).  Extra HBM traffic: 12 B per operand element once per gemm,
+// O((MK + KN) / (MNK)) of the MMA work — <2 % at 4096^3 and above.
+//
+// Kernel anatomy (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: per k-block, one cp.async.bulk.tensor per operand plane into the stage ring
+//   warp 1      MMA issuer (one lane): tcgen05.mma x (BLOCK_K/8) x TERMS per k-block, tcgen05.commit frees the stage;
+//               owns the TMEM allocation (2 accumulator buffers so the epilogue of tile i overlaps the mainloop of i+1)
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time, optional += C / + bias / relu, 128-bit stores
+//   barriers    full[STAGES], empty[STAGES] (TMA <-> MMA), tmem_full[2], tmem_empty[2] (MMA <-> epilogue)
+#include <cuda.h>
+
+#include "common.cuh"
+
+int sl_gemm_simt(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
+                 int accumulate);
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: a protocol bug must abort the kernel (sticky error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+            printf("sliced_b200 gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread on behalf of the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t <-> TMEM lane base+t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor, K-major operand tile [rows x BLOCK_K] fp32 written by TMA with SWIZZLE_(BLOCK_K*4)B:
+// row r sits at r * (BLOCK_K*4) bytes, 16-byte chunks XOR-swizzled within each group of 8 rows.
+//   bits [0,14)  start address >> 4         bits [16,30) leading byte offset >> 4 (unused for swizzled K-major; 1)
+//   bits [32,46) stride byte offset >> 4 = distance between 8-row groups        bits [46,48) descriptor version = 1
+//   bits [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+template <int BLOCK_K>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    constexpr uint64_t row_bytes = BLOCK_K * 4;
+    constexpr uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+// Instruction descriptor: D = F32 (bits[4,6)=1), A = B = TF32 (bits[7,10)=2, [10,13)=2), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ the MMA kernel
+constexpr int BLOCK_M = 128;
+constexpr int UMMA_K = 8;  // 32 bytes of tf32 per MMA
+constexpr int GEMM_THREADS = 192;
+constexpr int GROUP_M = 8;
+
+struct GemmParams {
+    int M, N, K;
+    float* C;           // [M x N] row-major
+    const float* bias;  // [N] or NULL
+    int accumulate;     // C += acc
+    int relu;           // C = (v >= 0) * v after bias
+    int c_vec_ok;       // N % 4 == 0 and C 16-byte aligned
+};
+
+template <int BLOCK_N, int BLOCK_K, int TERMS, int STAGES>
+struct GemmCfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
+    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers; 256 or 512 (power of two)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "stage ring does not fit in shared memory");
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+};
+
+template <int BLOCK_N, int BLOCK_K, int TERMS, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N, BLOCK_K, TERMS, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment: required by the 128B swizzle atom (8 rows x 128 B)
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_b_hi);
+        if (TERMS == 3) {
+            tma_prefetch_desc(&map_a_lo);
+            tma_prefetch_desc(&map_b_lo);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full_bar(s), 1);
+            mbar_init(tmem_empty_bar(s), 4);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+        const int group_size = GROUP_M * num_n;
+        const int group = tile / group_size;
+        const int first_m = group * GROUP_M;
+        const int gsz = min(num_m - first_m, GROUP_M);
+        const int in_group = tile - group * group_size;
+        m_blk = first_m + in_group % gsz;
+        n_blk = in_group / gsz;
+    };
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(tile, m_blk, n_blk);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+                    mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &map_a_hi, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+                    tma_load_2d(sb, &map_b_hi, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+                    if (TERMS == 3) {
+                        tma_load_2d(sa + Cfg::A_BYTES, &map_a_lo, full_bar(stage), kb * BLOCK_K, m_blk * BLOCK_M);
+                        tma_load_2d(sb + Cfg::B_BYTES, &map_b_lo, full_bar(stage), kb * BLOCK_K, n_blk * BLOCK_N);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+                    const uint64_t da_hi = make_smem_desc<BLOCK_K>(sa);
+                    const uint64_t db_hi = make_smem_desc<BLOCK_K>(sb);
+                    const uint64_t da_lo = make_smem_desc<BLOCK_K>(sa + Cfg::A_BYTES);
+                    const uint64_t db_lo = make_smem_desc<BLOCK_K>(sb + Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance the start address inside the swizzle atom
+                        const uint32_t first = (kb | k) == 0 ? 0u : 1u;
+                        if (TERMS == 3) {
+                            umma_tf32(tmem_d, da_lo + koff, db_hi + koff, idesc, first);
+                            umma_tf32(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                            umma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc, 1u);
+                        } else {
+                            umma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc, first);
+                        }
+                    }
+                    umma_commit(empty_bar(stage));  // stage is free once these MMAs have read it
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================================================= epilogue (warps 2..5)
+        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+        int local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BLOCK_M + quad * 32 + lane;
+            const bool row_ok = row < p.M;
+            float* crow = p.C + (size_t)row * p.N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
+                tmem_ld_32x32(taddr, r);
+                tmem_ld_wait();
+                const int n0 = n_blk * BLOCK_N + c * 32;
+                if (row_ok && n0 < p.N) {
+                    if (p.c_vec_ok && n0 + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                                   __uint_as_float(r[j + 3]));
+                            if (p.accumulate) {
+                                const float4 o = *reinterpret_cast<const float4*>(crow + n0 + j);
+                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                            }
+                            if (p.bias) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                            }
+                            if (p.relu) {
+                                v.x = (v.x >= 0.f ? 1.f : 0.f) * v.x; v.y = (v.y >= 0.f ? 1.f : 0.f) * v.y;
+                                v.z = (v.z >= 0.f ? 1.f : 0.f) * v.z; v.w = (v.w >= 0.f ? 1.f : 0.f) * v.w;
+                            }
+                            *reinterpret_cast<float4*>(crow + n0 + j) = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (n0 + j < p.N) {
+                                float v = __uint_as_float(r[j]);
+                                if (p.accumulate) v += crow[n0 + j];
+                                if (p.bias) v += __ldg(p.bias + n0 + j);
+                                if (p.relu) v = (v >= 0.f ? 1.f : 0.f) * v;
+                                crow[n0 + j] = v;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ operand prep kernels
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = rna_tf32(x);
+    if (!isfinite(hi)) {  // inf/nan input, or rounding overflowed: keep the top bits, no correction term
+        hi = isfinite(x) ? __uint_as_float(__float_as_uint(x) & 0xffffe000u) : x;
+        lo = isfinite(x) ? rna_tf32(x - hi) : 0.f;
+        return;
+    }
+    lo = rna_tf32(x - hi);
+}
+
+// src [R x K] row-major (K contiguous) -> hi / lo planes [R x ldp]; lo may be NULL (TF32 fast mode: hi = rna_tf32(x))
+__global__ void __launch_bounds__(256) prep_kmajor_kernel(size_t R, size_t K, size_t ldp, const float* __restrict__ src, float* __restrict__ hi,
+                                                          float* __restrict__ lo, int vec) {
+    if (vec) {
+        const size_t kp = K / 4;
+        const size_t total = R * kp;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const size_t r = i / kp, c = (i % kp) * 4;
+            const Pack<float> x = ld_stream(src + r * K + c);
+            Pack<float> h, l;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_tf32(x.v[e], h.v[e], l.v[e]);
+            st_stream(hi + r * ldp + c, h);
+            if (lo) st_stream(lo + r * ldp + c, l);
+        }
+    } else {
+        const size_t total = R * K;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+            const size_t r = i / K, c = i % K;
+            float h, l;
+            split_tf32(__ldg(src + i), h, l);
+            hi[r * ldp + c] = h;
+            if (lo) lo[r * ldp + c] = l;
+        }
+    }
+}
+
+// src [K x R] row-major (R contiguous) -> transposed hi / lo planes [R x ldp] (K contiguous)
+__global__ void __launch_bounds__(256) prep_transpose_kernel(size_t K, size_t R, size_t ldp, const float* __restrict__ src,
+                                                             float* __restrict__ hi, float* __restrict__ lo) {
+    __shared__ float tile[64][65];
+    const size_t tiles_r = (R + 63) / 64, tiles_k = (K + 63) / 64;
+    const size_t ntiles = tiles_r * tiles_k;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t k0 = (t / tiles_r) * 64, r0 = (t % tiles_r) * 64;
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+            const size_t k = k0 + threadIdx.y + i;
+#pragma unroll
+            for (int j = 0; j < 64; j += 32) {
+                const size_t r = r0 + threadIdx.x + j;
+                if (k < K && r < R) tile[threadIdx.y + i][threadIdx.x + j] = __ldg(src + k * R + r);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+            const size_t r = r0 + threadIdx.y + i;
+#pragma unroll
+            for (int j = 0; j < 64; j += 32) {
+                const size_t k = k0 + threadIdx.x + j;
+                if (k < K && r < R) {
+                    float h, l;
+                    split_tf32(tile[threadIdx.x + j][threadIdx.y + i], h, l);
+                    hi[r * ldp + k] = h;
+                    if (lo) lo[r * ldp + k] = l;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// K-major operand plane [rows x K] with leading dimension ld (floats); box = BLOCK_K x box_rows
+static int make_map(sl_ctx* ctx, CUtensorMap* map, const float* base, size_t rows, size_t K, size_t ld, int block_k, int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return sl_set_error(ctx, SL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sl_set_error(ctx, SL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%zu K=%zu ld=%zu", (int)r, rows, K, ld);
+    return SL_OK;
+}
+
+template <int BLOCK_N, int BLOCK_K, int TERMS, int STAGES>
+static int launch_cfg(sl_ctx* ctx, const GemmParams& p, const float* a_hi, const float* a_lo, size_t lda, const float* b_hi, const float* b_lo,
+                      size_t ldb) {
+    using Cfg = GemmCfg<BLOCK_N, BLOCK_K, TERMS, STAGES>;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_map(ctx, &ma_hi, a_hi, p.M, p.K, lda, BLOCK_K, BLOCK_M)) != SL_OK) return rc;
+    if ((rc = make_map(ctx, &mb_hi, b_hi, p.N, p.K, ldb, BLOCK_K, BLOCK_N)) != SL_OK) return rc;
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+    if (TERMS == 3) {
+        if ((rc = make_map(ctx, &ma_lo, a_lo, p.M, p.K, lda, BLOCK_K, BLOCK_M)) != SL_OK) return rc;
+        if ((rc = make_map(ctx, &mb_lo, b_lo, p.N, p.K, ldb, BLOCK_K, BLOCK_N)) != SL_OK) return rc;
+    }
+    auto kern = gemm_tf32_kernel<BLOCK_N, BLOCK_K, TERMS, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+    const int grid = num_tiles < ctx->num_sms ? num_tiles : ctx->num_sms;
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sl_set_error(ctx, SL_ERR_CUDA, "gemm_tf32_kernel launch: %s", cudaGetErrorString(e));
+    return SL_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
+}  // namespace
+
+// Runs the tensor-core kernel on prepared K-major planes: C[M x N] (=|+=) A[M x K] * B[N x K]^T (+ bias, relu).
+// a_lo / b_lo are NULL in TF32 mode.  lda / ldb in floats, multiples of 4, planes 16-byte aligned.
+int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const float* a_lo, size_t lda, const float* b_hi, const float* b_lo,
+                      size_t ldb, float* C, const float* bias, int accumulate, int relu) {
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu;
+    p.c_vec_ok = (N % 4 == 0) && sl_aligned16(C) && (!bias || sl_aligned16(bias));
+    const bool three = a_lo != nullptr;
+    // tile configuration: SLICED_GEMM_CFG = 0 auto | 1: 128x256x32 | 2: 128x256x16 (swizzle 64B, deeper ring) | 3: 128x128x32
+    int cfg = env_int("SLICED_GEMM_CFG", 0);
+    if (cfg == 0) {
+        const long tiles256 = (long)((M + 127) / 128) * ((N + 255) / 256);
+        cfg = (N <= 128 || tiles256 < ctx->num_sms) ? 3 : 1;
+    }
+    if (three) {
+        if (cfg == 1) return launch_cfg<256, 32, 3, 2>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        if (cfg == 2) return launch_cfg<256, 16, 3, 4>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        return launch_cfg<128, 32, 3, 3>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+    } else {
+        if (cfg == 1) return launch_cfg<256, 32, 1, 4>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        if (cfg == 2) return launch_cfg<256, 16, 1, 8>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        return launch_cfg<128, 32, 1, 6>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+    }
+}
+
+// Splits (and if needed transposes) one operand into K-major planes.  `rows` = M or N, `K` = contraction length.
+// k_contiguous: src is [rows x K]; otherwise src is [K x rows].
+int sl_gemm_prep_operand(sl_ctx* ctx, const float* src, size_t rows, size_t K, int k_contiguous, float* hi, float* lo, size_t ldp) {
+    const size_t cap = (size_t)ctx->num_sms * 8;
+    if (k_contiguous) {
+        const int vec = (K % 4 == 0) && sl_aligned16(src) && (ldp % 4 == 0);
+        const size_t total = vec ? rows * (K / 4) : rows * K;
+        size_t blocks = (total + 255) / 256;
+        SL_LAUNCH(ctx, prep_kmajor_kernel, (unsigned)(blocks < cap ? (blocks ? blocks : 1) : cap), 256, 0, rows, K, ldp, src, hi, lo, vec);
+    } else {
+        const size_t ntiles = ((rows + 63) / 64) * ((K + 63) / 64);
+        SL_LAUNCH(ctx, prep_transpose_kernel, (unsigned)(ntiles < cap ? (ntiles ? ntiles : 1) : cap), dim3(32, 8, 1), 0, K, rows, ldp, src, hi, lo);
+    }
+    return SL_OK;
+}
+
+static bool tc_eligible(size_t m, size_t n, size_t k) {
+    if (m > 0x7fffffff || n > 0x7fffffff || k > 0x7fffffff) return false;
+    if (env_int("SLICED_GEMM_TC_FORCE", 0)) return true;  // tests: push even tiny / ragged shapes through the tcgen05 kernel
+    // 128-row tcgen05 tiles: below this the CUDA-core kernel wins (and skinny heads like N = 10 stay exact fp32)
+    const size_t min_dim = (size_t)env_int("SLICED_GEMM_TC_MIN_DIM", 64);
+    return m >= min_dim && n >= min_dim && k >= 32 && (double)m * (double)n * (double)k >= (double)(1 << 22);
+}
+
+static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
+                        int accumulate, int mode, const float* bias, int relu) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (m == 0 || n == 0) return SL_OK;
+    SL_REQUIRE(ctx, c != nullptr, "NULL output");
+    if (k == 0) return accumulate ? SL_OK : sl_clear(ctx, c, m * n * sl_dtype_size(dtype));
+    SL_REQUIRE(ctx, a && b, "NULL operand");
+    if (mode < 0) mode = ctx->gemm_mode;
+    if (dtype != SL_F32 || mode == SL_GEMM_SIMT || !tc_eligible(m, n, k)) {
+        if (bias || relu) return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "fused epilogue needs the tensor-core path");
+        return sl_gemm_simt(ctx, dtype, trans_a, trans_b, m, n, k, a, b, c, accumulate);
+    }
+    const bool three = mode == SL_GEMM_3XTF32;
+    const size_t ldp = (k + 3) & ~size_t(3);
+    // A operand: contraction index contiguous iff !trans_a ; B operand ([N x K] wanted): contiguous iff trans_b
+    const bool a_direct = !three && !trans_a && (k % 4 == 0) && sl_aligned16(a);
+    const bool b_direct = !three && trans_b && (k % 4 == 0) && sl_aligned16(b);
+    const size_t a_plane = ((m * ldp * 4) + 255) & ~size_t(255);
+    const size_t b_plane = ((n * ldp * 4) + 255) & ~size_t(255);
+    const size_t need = (a_direct ? 0 : a_plane * (three ? 2 : 1)) + (b_direct ? 0 : b_plane * (three ? 2 : 1));
+    char* ws = nullptr;
+    if (need) {
+        int rc = sl_ws2_reserve(ctx, need, (void**)&ws);
+        if (rc != SL_OK) return rc;
+    }
+    const float *a_hi = (const float*)a, *a_lo = nullptr, *b_hi = (const float*)b, *b_lo = nullptr;
+    size_t lda = k, ldb = k;
+    char* cur = ws;
+    if (!a_direct) {
+        float* h = (float*)cur; cur += a_plane;
+        float* l = nullptr;
+        if (three) { l = (float*)cur; cur += a_plane; }
+        int rc = sl_gemm_prep_operand(ctx, (const float*)a, m, k, !trans_a, h, l, ldp);
+        if (rc != SL_OK) return rc;
+        a_hi = h; a_lo = l; lda = ldp;
+    }
+    if (!b_direct) {
+        float* h = (float*)cur; cur += b_plane;
+        float* l = nullptr;
+        if (three) { l = (float*)cur; cur += b_plane; }
+        int rc = sl_gemm_prep_operand(ctx, (const float*)b, n, k, trans_b, h, l, ldp);
+        if (rc != SL_OK) return rc;
+        b_hi = h; b_lo = l; ldb = ldp;
+    }
+    return sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, lda, b_hi, b_lo, ldb, (float*)c, bias, accumulate, relu);
+}
+
+extern "C" {
+
+int sl_gemm_ex(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
+               int accumulate, int mode) {
+    return gemm_ex_impl(ctx, dtype, trans_a, trans_b, m, n, k, a, b, c, accumulate, mode, nullptr, 0);
+}
+
+int sl_gemm(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, void* out, int mode) {
+    return gemm_ex_impl(ctx, dtype, 0, 0, m, n, k, lhs, rhs, out, 0, mode, nullptr, 0);
+}
+
+int sl_gemm_nt(sl_ctx* ctx, int dtype, size_t m, size_t n, size_t k, const void* a, const void* b, void* c, int mode) {
+    return gemm_ex_impl(ctx, dtype, 0, 1, m, n, k, a, b, c, 0, mode, nullptr, 0);
+}
+
+int sl_gemm_tn(sl_ctx* ctx, int dtype, size_t m, size_t n, size_t k, const void* a, const void* b, void* c, int mode) {
+    return gemm_ex_impl(ctx, dtype, 1, 0, m, n, k, a, b, c, 0, mode, nullptr, 0);
+}
+
+int sl_gemm_grad(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, void* lhs_grad, void* rhs_grad,
+                 const void* out_grad, int accumulate, int mode) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    SL_REQUIRE(ctx, out_grad != nullptr || m == 0 || n == 0, "NULL out_grad");
+    if (lhs_grad) {  // gemmT(m, k, n, out_grad, rhs, lhs_grad): lhs_grad[m x k] = out_grad[m x n] * rhs[k x n]^T
+        int rc = gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, lhs_grad, accumulate, mode, nullptr, 0);
+        if (rc != SL_OK) return rc;
+    }
+    if (rhs_grad) {  // Tgemm(k, n, m, lhs, out_grad, rhs_grad): rhs_grad[k x n] = lhs[m x k]^T * out_grad[m x n]
+        int rc = gemm_ex_impl(ctx, dtype, 1, 0, k, n, m, lhs, out_grad, rhs_grad, accumulate, mode, nullptr, 0);
+        if (rc != SL_OK) return rc;
+    }
+    return SL_OK;
+}
+
+}  // extern "C"

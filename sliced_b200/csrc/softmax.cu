@@ -1,0 +1,343 @@
+// softmax.cu — family S: row softmax forward (single pass: the row is read from HBM once, kept in registers,
+// written once = 8 B/elem) and its gradient in closed form  dx = s * (g - <s,g>)  (12 B/elem, SET).
+//
+// The reference computes the forward as 5 separate passes (max_cols, sub_cols, exp, sum_cols, div_cols —
+// src/ops2/softmax/cpu.rs:11-16) and the backward by materialising the F x F Jacobian per row
+// (src/ops2/softmax/grad/cpu.rs:40-60); the values agree up to fp rounding (tests pin the tolerance).
+//
+// Row ownership by feature count:  F <= 32: one thread per row;  F <= 1024: one warp per row;
+// otherwise one 256..1024-thread block per row with the row cached in registers (up to 8 packs per thread),
+// falling back to a re-reading loop for rows that do not fit or are not 16-byte aligned.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float m_exp(float a) { return expf(a); }
+__device__ __forceinline__ double m_exp(double a) { return exp(a); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T ov = __shfl_xor_sync(0xffffffffu, v, o);
+        v = ov > v ? ov : v;
+    }
+    return v;
+}
+
+// block-wide reductions over NW warps, fixed order, result broadcast to every thread
+template <typename T, bool IS_MAX>
+__device__ __forceinline__ T block_reduce(T v, T* s_buf) {
+    v = IS_MAX ? warp_max(v) : warp_sum(v);
+    const int w = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_buf[w] = v;
+    __syncthreads();
+    T r = s_buf[0];
+    for (int k = 1; k < nw; ++k) r = IS_MAX ? (s_buf[k] > r ? s_buf[k] : r) : (r + s_buf[k]);
+    return r;
+}
+
+// ---------------------------------------------------------------- forward
+// thread per row (tiny F, e.g. the 10-class head of the nn.rs MLP): the row stays in L1 between the passes
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_thread_kernel(size_t samples, size_t features, const T* __restrict__ x, T* __restrict__ out) {
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < samples; r += (size_t)gridDim.x * blockDim.x) {
+        const T* row = x + r * features;
+        T* orow = out + r * features;
+        T mx = row[0];
+        for (size_t c = 1; c < features; ++c) mx = row[c] > mx ? row[c] : mx;
+        T sum = T(0);
+        for (size_t c = 0; c < features; ++c) {
+            const T e = m_exp(row[c] - mx);
+            orow[c] = e;
+            sum += e;
+        }
+        for (size_t c = 0; c < features; ++c) orow[c] = orow[c] / sum;
+    }
+}
+
+// warp per row, F <= 1024: up to 32 values per lane in registers
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_warp_kernel(size_t samples, size_t features, const T* __restrict__ x, T* __restrict__ out) {
+    constexpr int MAXV = 32;
+    const int lane = threadIdx.x & 31;
+    const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = wid; r < samples; r += nwarps) {
+        const T* row = x + r * features;
+        T v[MAXV];
+        T mx = __ldg(row);
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const size_t c = (size_t)k * 32 + lane;
+            if (c < features) {
+                v[k] = __ldg(row + c);
+                mx = v[k] > mx ? v[k] : mx;
+            }
+        }
+        mx = warp_max(mx);
+        T sum = T(0);
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const size_t c = (size_t)k * 32 + lane;
+            if (c < features) {
+                v[k] = m_exp(v[k] - mx);
+                sum += v[k];
+            }
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const size_t c = (size_t)k * 32 + lane;
+            if (c < features) out[r * features + c] = v[k] / sum;
+        }
+    }
+}
+
+// block per row, row cached in registers as NP 128-bit packs per thread (features <= NP * VEC * blockDim.x)
+template <typename T, int NP>
+__global__ void __launch_bounds__(1024) softmax_block_kernel(size_t samples, size_t features, const T* __restrict__ x, T* __restrict__ out) {
+    constexpr int V = Pack<T>::N;
+    __shared__ T s_buf[32];
+    const size_t packs = features / V;
+    for (size_t r = blockIdx.x; r < samples; r += gridDim.x) {
+        const T* row = x + r * features;
+        Pack<T> p[NP];
+        T mx = __ldg(row);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const size_t i = (size_t)k * blockDim.x + threadIdx.x;
+            if (i < packs) {
+                p[k] = ld_stream(row + i * V);
+#pragma unroll
+                for (int e = 0; e < V; ++e) mx = p[k].v[e] > mx ? p[k].v[e] : mx;
+            }
+        }
+        mx = block_reduce<T, true>(mx, s_buf);
+        T sum = T(0);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const size_t i = (size_t)k * blockDim.x + threadIdx.x;
+            if (i < packs) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    p[k].v[e] = m_exp(p[k].v[e] - mx);
+                    sum += p[k].v[e];
+                }
+            }
+        }
+        sum = block_reduce<T, false>(sum, s_buf);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const size_t i = (size_t)k * blockDim.x + threadIdx.x;
+            if (i < packs) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) p[k].v[e] = p[k].v[e] / sum;
+                st_stream(out + r * features + i * V, p[k]);
+            }
+        }
+    }
+}
+
+// generic fallback: block per row, re-reads the row (any length / alignment)
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_loop_kernel(size_t samples, size_t features, const T* __restrict__ x, T* __restrict__ out) {
+    __shared__ T s_buf[32];
+    for (size_t r = blockIdx.x; r < samples; r += gridDim.x) {
+        const T* row = x + r * features;
+        T* orow = out + r * features;
+        T mx = __ldg(row);
+        for (size_t c = threadIdx.x; c < features; c += blockDim.x) {
+            const T v = __ldg(row + c);
+            mx = v > mx ? v : mx;
+        }
+        mx = block_reduce<T, true>(mx, s_buf);
+        T sum = T(0);
+        for (size_t c = threadIdx.x; c < features; c += blockDim.x) {
+            const T e = m_exp(__ldg(row + c) - mx);
+            orow[c] = e;
+            sum += e;
+        }
+        sum = block_reduce<T, false>(sum, s_buf);
+        for (size_t c = threadIdx.x; c < features; c += blockDim.x) orow[c] = orow[c] / sum;
+    }
+}
+
+// ---------------------------------------------------------------- backward (closed form, SET)
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_grad_thread_kernel(size_t samples, size_t features, T* __restrict__ xg, const T* __restrict__ s,
+                                                                  const T* __restrict__ g) {
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < samples; r += (size_t)gridDim.x * blockDim.x) {
+        const T* sr = s + r * features;
+        const T* gr = g + r * features;
+        T dot = T(0);
+        for (size_t c = 0; c < features; ++c) dot += sr[c] * gr[c];
+        for (size_t c = 0; c < features; ++c) xg[r * features + c] = sr[c] * (gr[c] - dot);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_grad_warp_kernel(size_t samples, size_t features, T* __restrict__ xg, const T* __restrict__ s,
+                                                                const T* __restrict__ g) {
+    constexpr int MAXV = 32;
+    const int lane = threadIdx.x & 31;
+    const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = wid; r < samples; r += nwarps) {
+        T sv[MAXV], gv[MAXV];
+        T dot = T(0);
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const size_t c = (size_t)k * 32 + lane;
+            if (c < features) {
+                sv[k] = __ldg(s + r * features + c);
+                gv[k] = __ldg(g + r * features + c);
+                dot += sv[k] * gv[k];
+            }
+        }
+        dot = warp_sum(dot);
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const size_t c = (size_t)k * 32 + lane;
+            if (c < features) xg[r * features + c] = sv[k] * (gv[k] - dot);
+        }
+    }
+}
+
+template <typename T, int NP>
+__global__ void __launch_bounds__(1024) softmax_grad_block_kernel(size_t samples, size_t features, T* __restrict__ xg, const T* __restrict__ s,
+                                                                  const T* __restrict__ g) {
+    constexpr int V = Pack<T>::N;
+    __shared__ T s_buf[32];
+    const size_t packs = features / V;
+    for (size_t r = blockIdx.x; r < samples; r += gridDim.x) {
+        Pack<T> ps[NP], pg[NP];
+        T dot = T(0);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const size_t i = (size_t)k * blockDim.x + threadIdx.x;
+            if (i < packs) {
+                ps[k] = ld_stream(s + r * features + i * V);
+                pg[k] = ld_stream(g + r * features + i * V);
+#pragma unroll
+                for (int e = 0; e < V; ++e) dot += ps[k].v[e] * pg[k].v[e];
+            }
+        }
+        dot = block_reduce<T, false>(dot, s_buf);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const size_t i = (size_t)k * blockDim.x + threadIdx.x;
+            if (i < packs) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) ps[k].v[e] = ps[k].v[e] * (pg[k].v[e] - dot);
+                st_stream(xg + r * features + i * V, ps[k]);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_grad_loop_kernel(size_t samples, size_t features, T* __restrict__ xg, const T* __restrict__ s,
+                                                                const T* __restrict__ g) {
+    __shared__ T s_buf[32];
+    for (size_t r = blockIdx.x; r < samples; r += gridDim.x) {
+        T dot = T(0);
+        for (size_t c = threadIdx.x; c < features; c += blockDim.x) dot += __ldg(s + r * features + c) * __ldg(g + r * features + c);
+        dot = block_reduce<T, false>(dot, s_buf);
+        for (size_t c = threadIdx.x; c < features; c += blockDim.x)
+            xg[r * features + c] = __ldg(s + r * features + c) * (__ldg(g + r * features + c) - dot);
+    }
+}
+
+// pick (threads, NP) so that NP * VEC * threads >= features with threads in {256, 512, 1024}, NP in {1,2,4,8}
+struct BlockPlan {
+    int threads;
+    int np;
+};
+template <typename T>
+static BlockPlan plan_block(size_t features, int max_np) {
+    const size_t packs = features / Pack<T>::N;
+    for (int np = 1; np <= max_np; np *= 2)
+        for (int th = 256; th <= 1024; th *= 2)
+            if ((size_t)np * th >= packs) return {th, np};
+    return {0, 0};
+}
+
+template <typename T>
+int softmax_t(sl_ctx* ctx, size_t samples, size_t features, const void* x, void* out) {
+    const size_t cap = (size_t)ctx->num_sms * 8;
+    if (features <= 32) {
+        size_t blocks = (samples + 255) / 256;
+        SL_LAUNCH(ctx, (softmax_thread_kernel<T>), (unsigned)(blocks < cap ? blocks : cap), 256, 0, samples, features, (const T*)x, (T*)out);
+        return SL_OK;
+    }
+    if (features <= 1024) {
+        size_t blocks = (samples + 7) / 8;
+        SL_LAUNCH(ctx, (softmax_warp_kernel<T>), (unsigned)(blocks < cap ? blocks : cap), 256, 0, samples, features, (const T*)x, (T*)out);
+        return SL_OK;
+    }
+    const bool vec = (features % Pack<T>::N == 0) && sl_aligned16(x) && sl_aligned16(out);
+    BlockPlan bp = vec ? plan_block<T>(features, 8) : BlockPlan{0, 0};
+    const unsigned grid = (unsigned)(samples < cap * 4 ? samples : cap * 4);
+    if (bp.np == 1) SL_LAUNCH(ctx, (softmax_block_kernel<T, 1>), grid, bp.threads, 0, samples, features, (const T*)x, (T*)out);
+    else if (bp.np == 2) SL_LAUNCH(ctx, (softmax_block_kernel<T, 2>), grid, bp.threads, 0, samples, features, (const T*)x, (T*)out);
+    else if (bp.np == 4) SL_LAUNCH(ctx, (softmax_block_kernel<T, 4>), grid, bp.threads, 0, samples, features, (const T*)x, (T*)out);
+    else if (bp.np == 8) SL_LAUNCH(ctx, (softmax_block_kernel<T, 8>), grid, bp.threads, 0, samples, features, (const T*)x, (T*)out);
+    else SL_LAUNCH(ctx, (softmax_loop_kernel<T>), grid, 256, 0, samples, features, (const T*)x, (T*)out);
+    return SL_OK;
+}
+
+template <typename T>
+int softmax_grad_t(sl_ctx* ctx, size_t samples, size_t features, void* xg, const void* s, const void* g) {
+    const size_t cap = (size_t)ctx->num_sms * 8;
+    if (features <= 32) {
+        size_t blocks = (samples + 255) / 256;
+        SL_LAUNCH(ctx, (softmax_grad_thread_kernel<T>), (unsigned)(blocks < cap ? blocks : cap), 256, 0, samples, features, (T*)xg, (const T*)s,
+                  (const T*)g);
+        return SL_OK;
+    }
+    if (features <= 1024) {
+        size_t blocks = (samples + 7) / 8;
+        SL_LAUNCH(ctx, (softmax_grad_warp_kernel<T>), (unsigned)(blocks < cap ? blocks : cap), 256, 0, samples, features, (T*)xg, (const T*)s,
+                  (const T*)g);
+        return SL_OK;
+    }
+    const bool vec = (features % Pack<T>::N == 0) && sl_aligned16(xg) && sl_aligned16(s) && sl_aligned16(g);
+    BlockPlan bp = vec ? plan_block<T>(features, 4) : BlockPlan{0, 0};
+    const unsigned grid = (unsigned)(samples < cap * 4 ? samples : cap * 4);
+    if (bp.np == 1) SL_LAUNCH(ctx, (softmax_grad_block_kernel<T, 1>), grid, bp.threads, 0, samples, features, (T*)xg, (const T*)s, (const T*)g);
+    else if (bp.np == 2) SL_LAUNCH(ctx, (softmax_grad_block_kernel<T, 2>), grid, bp.threads, 0, samples, features, (T*)xg, (const T*)s, (const T*)g);
+    else if (bp.np == 4) SL_LAUNCH(ctx, (softmax_grad_block_kernel<T, 4>), grid, bp.threads, 0, samples, features, (T*)xg, (const T*)s, (const T*)g);
+    else SL_LAUNCH(ctx, (softmax_grad_loop_kernel<T>), grid, 256, 0, samples, features, (T*)xg, (const T*)s, (const T*)g);
+    return SL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sl_softmax(sl_ctx* ctx, int dtype, size_t samples, size_t features, const void* x, void* out) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (samples == 0 || features == 0) return SL_OK;
+    SL_REQUIRE(ctx, x && out, "NULL pointer");
+    SL_DISPATCH_FLOAT(ctx, dtype, T, return softmax_t<T>(ctx, samples, features, x, out));
+    return SL_OK;
+}
+
+int sl_softmax_grad(sl_ctx* ctx, int dtype, size_t samples, size_t features, void* x_grad, const void* out, const void* out_grad) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (samples == 0 || features == 0) return SL_OK;
+    SL_REQUIRE(ctx, x_grad && out && out_grad, "NULL pointer");
+    SL_DISPATCH_FLOAT(ctx, dtype, T, return softmax_grad_t<T>(ctx, samples, features, x_grad, out, out_grad));
+    return SL_OK;
+}
+
+}  // extern "C"

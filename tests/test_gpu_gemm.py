@@ -1,0 +1,185 @@
+"""
+gemm / trans_gemm / gemm_grad parity on the GPU (through the C ABI).
+
+Stated tolerances (BASELINE.json north_star: "K-scaled for gemm"), inputs U(-1,1):
+  * SL_GEMM_SIMT   : BIT-EXACT vs the oracle's restatement (sequential-k mul+add, no FMA on either side)
+  * SL_GEMM_3XTF32 : max |c - truth_fp64| <= 4 * K * 2^-24      (fp32-class; also held to <= 16x the oracle sgemm's own error)
+  * SL_GEMM_TF32   : max |c - truth_fp64| <= 8 * sqrt(K) * 2^-11 (reported, loose gate: flagged fast mode)
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import sliced_b200 as S
+    return S.Context(0)
+
+
+@pytest.fixture(autouse=True)
+def force_tensor_core_path(monkeypatch):
+    """route every f32 gemm of this module through the tcgen05 kernel, whatever its size (default dispatch sends tiny
+    problems to the CUDA-core kernel)"""
+    monkeypatch.setenv("SLICED_GEMM_TC_FORCE", "1")
+
+
+def truth(ta, tb, m, n, k, a, b):
+    A = a.reshape(k, m).T if ta else a.reshape(m, k)
+    B = b.reshape(n, k).T if tb else b.reshape(k, n)
+    return (A.astype(np.float64) @ B.astype(np.float64)).ravel()
+
+
+def run(ctx, ta, tb, m, n, k, a, b, mode, c0=None, accumulate=False):
+    dc = ctx.array(c0) if c0 is not None else None
+    return ctx.gemm_ex(ta, tb, m, n, k, ctx.array(a), ctx.array(b), dc, accumulate, mode).numpy()
+
+
+SMALL = [(1, 1, 1), (4, 3, 2), (5, 10, 7), (64, 64, 64), (65, 63, 33), (130, 70, 257), (1000, 64, 64), (33, 129, 1000)]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int32])
+@pytest.mark.parametrize("shape", SMALL)
+@pytest.mark.parametrize("trans", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_simt_bit_exact_vs_oracle(ctx, dt, shape, trans):
+    import sliced_b200 as S
+    m, n, k = shape
+    ta, tb = trans
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    if dt == np.int32:
+        a, b = rng.integers(-9, 9, m * k).astype(dt), rng.integers(-9, 9, k * n).astype(dt)
+        c0 = rng.integers(-9, 9, m * n).astype(dt)
+    else:
+        a, b = rng.uniform(-1, 1, m * k).astype(dt), rng.uniform(-1, 1, k * n).astype(dt)
+        c0 = rng.uniform(-1, 1, m * n).astype(dt)
+    ref = O.gemm_ex(ta, tb, m, n, k, a, b)
+    got = run(ctx, ta, tb, m, n, k, a, b, S.GEMM_SIMT)
+    assert np.array_equal(got, ref), f"max diff {np.max(np.abs(got.astype(np.float64) - ref))}"
+    ref_acc = O.gemm_ex(ta, tb, m, n, k, a, b, c0.copy(), accumulate=True)
+    got_acc = run(ctx, ta, tb, m, n, k, a, b, S.GEMM_SIMT, c0, True)
+    assert np.array_equal(got_acc, ref_acc)
+
+
+TC_SHAPES = [
+    (1, 1, 1), (4, 3, 2), (17, 5, 9), (128, 128, 32), (128, 256, 64), (256, 128, 128), (128, 128, 4096),
+    (64, 64, 1024), (130, 70, 260), (200, 300, 100), (1000, 64, 64), (384, 520, 36), (129, 257, 513),
+    (512, 512, 512), (1024, 1024, 1024), (1000, 1000, 1000), (777, 1234, 555), (2048, 256, 64), (4096, 128, 32),
+    (257, 1030, 31 + 33), (300, 200, 1002),  # K % 4 != 0 -> padded planes
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("trans", [(0, 0), (0, 1), (1, 0)], ids=["NN", "NT", "TN"])
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
+def test_tensor_core_gemm(ctx, shape, trans, mode):
+    import sliced_b200 as S
+    m, n, k = shape
+    ta, tb = trans
+    md = S.GEMM_3XTF32 if mode == "3xtf32" else S.GEMM_TF32
+    rng = np.random.default_rng(42 + m + n + k)
+    a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
+    t = truth(ta, tb, m, n, k, a, b)
+    got = run(ctx, ta, tb, m, n, k, a, b, md)
+    err = np.max(np.abs(got - t))
+    if mode == "3xtf32":
+        ref = O.gemm_ex(ta, tb, m, n, k, a, b)
+        ref_err = np.max(np.abs(ref - t))
+        assert err <= 4 * k * 2.0 ** -24, f"3xTF32 err {err} (oracle sgemm err {ref_err})"
+        assert err <= 16 * ref_err + 2.0 ** -22, f"3xTF32 err {err} vs oracle sgemm err {ref_err}"
+    else:
+        assert err <= 8 * np.sqrt(k) * 2.0 ** -11, f"TF32 err {err}"
+
+
+@pytest.mark.parametrize("cfg", ["1", "2", "3"])
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
+def test_tile_configs(cfg, mode):
+    """every tile configuration of the tcgen05 kernel (SLICED_GEMM_CFG) gives the same answers; tails included"""
+    import sliced_b200 as S
+    os.environ["SLICED_GEMM_CFG"] = cfg
+    try:
+        ctx = S.Context(0)
+        md = S.GEMM_3XTF32 if mode == "3xtf32" else S.GEMM_TF32
+        for (m, n, k) in [(128, 256, 128), (640, 768, 1024), (300, 700, 200), (4096, 512, 96), (1111, 2222, 333)]:
+            rng = np.random.default_rng(m + n + k)
+            a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
+            t = truth(0, 0, m, n, k, a, b)
+            got = run(ctx, 0, 0, m, n, k, a, b, md)
+            err = np.max(np.abs(got - t))
+            assert err <= (4 * k * 2.0 ** -24 if mode == "3xtf32" else 8 * np.sqrt(k) * 2.0 ** -11), (cfg, mode, m, n, k, err)
+        ctx.close()
+    finally:
+        os.environ.pop("SLICED_GEMM_CFG", None)
+
+
+def test_accumulate_and_set_semantics(ctx):
+    """gemm is SET even into a junk-filled (Cached) buffer; accumulate=1 adds (the OpenCL reference's gemm_grad)"""
+    import sliced_b200 as S
+    m, n, k = 300, 260, 128
+    rng = np.random.default_rng(0)
+    a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
+    c0 = rng.uniform(-5, 5, m * n).astype(np.float32)
+    t = truth(0, 0, m, n, k, a, b)
+    got = run(ctx, 0, 0, m, n, k, a, b, S.GEMM_3XTF32, c0, False)
+    assert np.max(np.abs(got - t)) <= 4 * k * 2.0 ** -24
+    got = run(ctx, 0, 0, m, n, k, a, b, S.GEMM_3XTF32, c0, True)
+    assert np.max(np.abs(got - (t + c0))) <= 4 * k * 2.0 ** -24 + 2.0 ** -21
+
+
+def test_gemm_grad_matches_oracle(ctx):
+    import sliced_b200 as S
+    m, k, n = 384, 200, 136
+    rng = np.random.default_rng(11)
+    lhs, rhs = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
+    og = rng.uniform(-1, 1, m * n).astype(np.float32)
+    lg_ref, rg_ref = np.zeros_like(lhs), np.zeros_like(rhs)
+    O.gemm_grad(m, k, n, lhs, rhs, lg_ref, rg_ref, og)
+    for mode in (S.GEMM_3XTF32, S.GEMM_SIMT):
+        dl, dr = ctx.array(rng.uniform(-3, 3, m * k).astype(np.float32)), ctx.array(rng.uniform(-3, 3, k * n).astype(np.float32))
+        ctx.gemm_grad(m, k, n, ctx.array(lhs), ctx.array(rhs), dl, dr, ctx.array(og), False, mode)  # SET over junk
+        assert np.max(np.abs(dl.numpy() - lg_ref)) <= 4 * n * 2.0 ** -24 * 2
+        assert np.max(np.abs(dr.numpy() - rg_ref)) <= 4 * m * 2.0 ** -24 * 2
+    # requires_grad() == false on one side: NULL pointer skips it
+    dl = ctx.array(np.zeros(m * k, np.float32))
+    ctx.gemm_grad(m, k, n, ctx.array(lhs), ctx.array(rhs), dl, None, ctx.array(og), False, S.GEMM_3XTF32)
+    assert np.max(np.abs(dl.numpy() - lg_ref)) <= 4 * n * 2.0 ** -24 * 2
+
+
+def test_3xtf32_is_fp32_class_on_ill_scaled_data(ctx):
+    """values spanning 2^-10..2^10: plain TF32 loses ~3 decimal digits, 3xTF32 must not"""
+    import sliced_b200 as S
+    m = n = 256; k = 512
+    rng = np.random.default_rng(3)
+    a = (rng.uniform(-1, 1, m * k) * 2.0 ** rng.integers(-10, 10, m * k)).astype(np.float32)
+    b = (rng.uniform(-1, 1, k * n) * 2.0 ** rng.integers(-10, 10, k * n)).astype(np.float32)
+    t = truth(0, 0, m, n, k, a, b)
+    scale = np.abs(a.reshape(m, k)).astype(np.float64) @ np.abs(b.reshape(k, n)).astype(np.float64)
+    e3 = np.max(np.abs(run(ctx, 0, 0, m, n, k, a, b, S.GEMM_3XTF32) - t) / scale.ravel())
+    e1 = np.max(np.abs(run(ctx, 0, 0, m, n, k, a, b, S.GEMM_TF32) - t) / scale.ravel())
+    es = np.max(np.abs(O.gemm_ex(0, 0, m, n, k, a, b) - t) / scale.ravel())
+    assert e3 <= 2.0 ** -21, (e3, e1, es)
+    assert e1 > 16 * e3, "TF32 fast mode is not supposed to be this accurate: is the 3-term path really different?"
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
+def test_full_size_sampled(ctx, mode):
+    """BASELINE gemm sweep top size region: 8192^3 checked on a random sample of output entries against fp64 dot products"""
+    import sliced_b200 as S
+    m = n = k = 8192
+    md = S.GEMM_3XTF32 if mode == "3xtf32" else S.GEMM_TF32
+    rng = np.random.default_rng(42)
+    a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
+    da, db = ctx.array(a), ctx.array(b)
+    c = ctx.gemm(m, k, n, da, db, mode=md).numpy().reshape(m, n)
+    rows, cols = rng.integers(0, m, 48), rng.integers(0, n, 48)
+    rows[:4] = [0, m - 1, 127, 128]; cols[:4] = [0, n - 1, 255, 256]
+    t = a.reshape(m, k)[rows].astype(np.float64) @ b.reshape(k, n)[:, cols].astype(np.float64)
+    err = np.max(np.abs(c[np.ix_(rows, cols)] - t))
+    assert err <= (4 * k * 2.0 ** -24 if mode == "3xtf32" else 8 * np.sqrt(k) * 2.0 ** -11), err
+    # linearity: (2A)B == 2(AB) exactly (power-of-two scaling commutes with every rounding step)
+    c2 = ctx.gemm(m, k, n, ctx.array(a * 2), db, mode=md).numpy().reshape(m, n)
+    assert np.array_equal(c2[rows], 2 * c[rows])
