@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of sliced_b200 (contract: one JSON line on stdout from rank 0).
+
+Workload (BASELINE.json configs[4], the config its metric "MLP train-step samples/s @1/2/4/8 GPU" is quoted on; it fits
+one GPU): examples/nn.rs MLP 4096-4096-4096-10, softmax + categorical cross-entropy, SGD lr 0.1, f32, GLOBAL batch 65536,
+data-parallel along the batch with one NCCL sum-all-reduce of the 134 MB gradient bucket per step (strong scaling).
+One "step" = zero_grad -> 3 x (gemm, add_row_mut, relu|softmax) -> accuracy + loss -> backward_with (tape) -> all-reduce ->
+SGD, exactly the op sequence of examples/nn.rs:184-237, run through the C++ host layer over the C ABI.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling strong|weak] [--gemm-mode 3xtf32|tf32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+value   whole-job samples/s with the batch already resident in HBM (device-timed with CUDA events, max over ranks)
+e2e     the same metric through the host-layer API with HOST buffers: every step copies its inputs from pinned host memory
+        and reads the step's loss/accuracy back
+roofline      the dominant kernel (tcgen05 gemm): per-launch CUDA events recorded live during the timed steps
+cpu_baseline  the reference's CPU path (oracle replay + OpenBLAS sgemm, what custos' `blas` feature links) on the host cores,
+              on a bounded sample of the same workload — a reported baseline, not the target
+--impl reference   times that CPU path alone (rank 0 only), same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+DIMS = [4096, 4096, 4096, 10]
+GLOBAL_BATCH = 65536
+LR = 0.1
+METRIC = "mlp_train_step_samples_per_s"
+UNIT = "samples/s"
+WORKLOAD = "examples/nn.rs MLP 4096-4096-4096-10 softmax+cce SGD(lr 0.1) f32, global batch 65536, data-parallel over the batch"
+
+
+def step_flops(batch: int) -> float:
+    """algorithmic gemm flops of one training step: fwd 2B(d0 d1 + d1 d2 + d2 d3), bwd dW for all layers + dA for layers > 0"""
+    f = 0.0
+    for l in range(len(DIMS) - 1):
+        f += 2.0 * batch * DIMS[l] * DIMS[l + 1]          # forward
+        f += 2.0 * batch * DIMS[l] * DIMS[l + 1]          # dW
+        if l > 0:
+            f += 2.0 * batch * DIMS[l] * DIMS[l + 1]      # dA (x is no_grad: layer 0 has none)
+    return f
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), power_w_max=max(pw), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def make_host_problem(batch: int, seed: int = 7):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (batch, DIMS[0])).astype(np.float32)      # shipped data is pixel/255 (nn.rs:170-173)
+    labels = rng.integers(0, DIMS[-1], batch).astype(np.int32)
+    y = np.zeros((batch, DIMS[-1]), np.float32)
+    y[np.arange(batch), labels] = 1.0
+    return x, y, labels
+
+
+def make_params(seed: int = 11):
+    rng = np.random.default_rng(seed)
+    W = [rng.uniform(-0.1, 0.1, DIMS[i] * DIMS[i + 1]).astype(np.float32) for i in range(len(DIMS) - 1)]   # nn.rs:26
+    B = [np.zeros(DIMS[i + 1], np.float32) for i in range(len(DIMS) - 1)]                                   # nn.rs:33
+    return W, B
+
+
+def cpu_reference_rate(steps: int, warmup: int, sample_batch: int):
+    """The reference's own CPU implementation of the step: the oracle's op-by-op replay with OpenBLAS sgemm on all host cores."""
+    import oracle as O
+    cores = os.cpu_count() or 1
+    blas = O.use_openblas(cores)
+    x, y, labels = make_host_problem(sample_batch)
+    W, B = make_params()
+    xs, ys = x.ravel(), y.ravel()
+    for _ in range(warmup):
+        O.mlp_step(0, DIMS, xs, ys, labels, W, B, LR, grad_rows=GLOBAL_BATCH)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.mlp_step(0, DIMS, xs, ys, labels, W, B, LR, grad_rows=GLOBAL_BATCH)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    O.use_naive_gemm()
+    return dict(value=sample_batch / dt, unit=UNIT, cores=cores if blas else 1, kind="port",
+                sample=f"{steps} step(s) of the same MLP on a {sample_batch}-sample batch ({dt * 1e3:.0f} ms/step); "
+                       f"gemm = OpenBLAS sgemm on {cores if blas else 1} thread(s), every other op = single-thread oracle loop "
+                       f"(the reference's slice loops are single-threaded)"), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), min(args.warmup, 1)
+    cb, dt = cpu_reference_rate(steps, warmup, args.cpu_sample)
+    line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup, ms_per_step=dt * 1e3,
+                higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, global_batch=GLOBAL_BATCH, sample_batch=args.cpu_sample, parallelism="cpu"),
+                cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import sliced_b200 as S
+    from sliced_b200 import capi
+    from sliced_b200.host import CUDA, Mlp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    stream = torch.cuda.current_stream()
+    dev = CUDA(local_rank, cached=True, stream=stream.cuda_stream)
+    dev.set_gemm_mode(S.GEMM_TF32 if args.gemm_mode == "tf32" else S.GEMM_3XTF32)
+    lib = capi.load()
+    ctx = dev.ctx_handle
+
+    if world > 1:  # one NCCL communicator for the gradient exchange, id shipped through torch.distributed
+        idbuf = (C.c_char * 128)()
+        if rank == 0:
+            capi.check(None, lib.sl_comm_unique_id(idbuf))
+        t = torch.frombuffer(bytearray(bytes(idbuf)), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        idb = bytes(t.cpu().numpy().tobytes())
+        capi.check(ctx, lib.sl_comm_init_rank(ctx, world, rank, idb))
+
+    batch = GLOBAL_BATCH // world if args.scaling == "strong" else GLOBAL_BATCH
+    global_batch = batch * world
+    # synthetic data of the config's shape: this rank's shard (seeded per rank), pinned on the host for the e2e leg
+    g = torch.Generator(device="cuda").manual_seed(7 + rank)
+    x_dev = torch.empty(batch, DIMS[0], device="cuda").uniform_(0, 1, generator=g)
+    labels_dev = torch.randint(0, DIMS[-1], (batch,), device="cuda", generator=g, dtype=torch.int32)
+    y_dev = torch.zeros(batch, DIMS[-1], device="cuda")
+    y_dev[torch.arange(batch, device="cuda"), labels_dev.long()] = 1.0
+    x_pin = torch.empty(batch, DIMS[0], pin_memory=True).copy_(x_dev)
+    y_pin = torch.empty(batch, DIMS[-1], pin_memory=True).copy_(y_dev)
+    l_pin = torch.empty(batch, dtype=torch.int32, pin_memory=True).copy_(labels_dev)
+    torch.cuda.synchronize()
+
+    mlp = Mlp(dev, DIMS, 0)
+    W, B = make_params()  # identical seeded init on every rank (replicas stay bit-identical: same summed gradients)
+    for l in range(len(DIMS) - 1):
+        mlp.weights(l).write(W[l])
+        mlp.bias(l).write(B[l])
+
+    bx = dev.wrap(x_dev.data_ptr(), x_dev.numel()).no_grad()
+    by = dev.wrap(y_dev.data_ptr(), y_dev.numel()).no_grad()
+    bl = dev.wrap(labels_dev.data_ptr(), batch, np.int32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def resident_step(metrics: bool):
+        return mlp.step(bx, by, bl, batch, LR, grad_rows=global_batch, want_metrics=metrics)
+
+    # ---------------- device-resident leg (`value`)
+    for _ in range(max(args.warmup, 3)):
+        resident_step(True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = dev.launches
+    capi.check(ctx, lib.sl_ctx_profile_begin(ctx))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        resident_step(False)   # loss / accuracy are still computed on the device every step; only the host read is outside `value`
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    n_l, t_ms, t_fl = C.c_uint64(0), C.c_double(0), C.c_double(0)
+    capi.check(ctx, lib.sl_ctx_profile_end(ctx, C.byref(n_l), C.byref(t_ms), C.byref(t_fl)))
+    launches = dev.launches - launches0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ms_total / args.steps)
+    value = global_batch / (ms_step * 1e-3)
+    loss_sum, correct = resident_step(True)
+
+    # ---------------- end-to-end leg: host buffers in, loss/accuracy out, every step
+    xs, ys, ls = dev.zeros(batch * DIMS[0]), dev.zeros(batch * DIMS[-1]), dev.zeros(batch, np.int32)
+    xs.no_grad(); ys.no_grad()
+    h2d = x_pin.numel() * 4 + y_pin.numel() * 4 + l_pin.numel() * 4
+    d2h = 8
+
+    def e2e_step():
+        capi.check(ctx, lib.sl_write(ctx, xs.ptr, x_pin.data_ptr(), x_pin.numel() * 4))
+        capi.check(ctx, lib.sl_write(ctx, ys.ptr, y_pin.data_ptr(), y_pin.numel() * 4))
+        capi.check(ctx, lib.sl_write(ctx, ls.ptr, l_pin.data_ptr(), l_pin.numel() * 4))
+        return mlp.step(xs, ys, ls, batch, LR, grad_rows=global_batch, want_metrics=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    barrier()
+
+    if rank == 0:
+        pk = peaks()
+        tf32_peak = pk["bf16_sustained"] / 2.0
+        eff = (t_fl.value / (t_ms.value * 1e-3)) / 1e12 if t_ms.value > 0 else 0.0
+        mult = 1 if args.gemm_mode == "tf32" else 3
+        roofline = dict(bound="tensor", kernel="gemm_tf32_kernel (tcgen05 kind::tf32, TMA, TMEM)", achieved=eff, peak=tf32_peak, unit="TFLOP/s",
+                        frac=eff / tf32_peak, traffic=None,
+                        peak_src=f"{pk['src']}: bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate); kernel timed inside a long step",
+                        issued_tflops=eff * mult, pipe_util=eff * mult / tf32_peak,
+                        note=f"achieved = algorithmic 2MNK flops of the {n_l.value} tensor-core gemm launches / their summed CUDA-event time "
+                             f"({t_ms.value / max(n_l.value, 1):.3f} ms avg); 3xTF32 issues {mult}x those flops to the tensor pipe",
+                        gemm_share_of_step=t_ms.value / ms_total if ms_total > 0 else None,
+                        step_effective_tflops=step_flops(batch) / (ms_total / args.steps * 1e-3) / 1e12)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
+                    higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=WORKLOAD, global_batch=global_batch, per_gpu_batch=batch, parallelism=f"dp{world}",
+                                gemm_mode=args.gemm_mode, l2="inputs (>= 128 MiB per operand at every N) exceed the 126 MB L2; no flush needed"),
+                    e2e=dict(value=global_batch / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roofline,
+                    last_step=dict(mean_loss=loss_sum / batch, accuracy=correct / batch))
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_reference_rate(1, 0, args.cpu_sample)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    del mlp
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
+    ap.add_argument("--gemm-mode", choices=["3xtf32", "tf32"], default="3xtf32")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,12 @@ int sl_ctx_set_gemm_mode(sl_ctx* ctx, int mode);
 /* Number of kernels this library launched on ctx since creation (bench.py's gpu_launches). */
 uint64_t sl_ctx_launch_count(sl_ctx* ctx);
 
+/* Per-launch CUDA-event timing of the tensor-core gemm kernel (bench.py's live roofline measurement): between begin and
+ * end every MMA-kernel launch is bracketed by two events on the ctx stream; end synchronises and returns the number of
+ * launches, their summed device time (ms) and their summed algorithmic flops (2*M*N*K each). */
+int sl_ctx_profile_begin(sl_ctx* ctx);
+int sl_ctx_profile_end(sl_ctx* ctx, uint64_t* n_launches, double* total_ms, double* total_flops);
+
 /* ref: custos `Alloc<T>::alloc` / `OnDropBuffer` † */
 int sl_malloc(sl_ctx* ctx, size_t bytes, void** out_dptr);
 int sl_free(sl_ctx* ctx, void* dptr);

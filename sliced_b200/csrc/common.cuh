@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 #include <type_traits>
 
 #include "../../include/sliced_b200.h"
@@ -23,6 +24,10 @@ struct sl_ctx {
     size_t ws_bytes = 0;
     void* ws2 = nullptr;  // second scratch region (gemm planes live here so reductions can run concurrently in-order)
     size_t ws2_bytes = 0;
+    // optional per-launch event timing of the gemm MMA kernel (sl_ctx_profile_begin / _end)
+    bool profiling = false;
+    struct ProfRec { cudaEvent_t a, b; double flops; };
+    std::vector<ProfRec> prof;
     // NCCL (dlopen'ed lazily)
     void* nccl_comm = nullptr;
     int nranks = 1;

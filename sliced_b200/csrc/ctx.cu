@@ -122,6 +122,34 @@ int sl_ctx_set_gemm_mode(sl_ctx* ctx, int mode) {
     return SL_OK;
 }
 
+int sl_ctx_profile_begin(sl_ctx* ctx) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    ctx->prof.clear();
+    ctx->profiling = true;
+    return SL_OK;
+}
+
+int sl_ctx_profile_end(sl_ctx* ctx, uint64_t* n_launches, double* total_ms, double* total_flops) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    ctx->profiling = false;
+    SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0, fl = 0;
+    for (auto& r : ctx->prof) {
+        float t = 0;
+        SL_CUDA(ctx, cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t;
+        fl += r.flops;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    if (n_launches) *n_launches = ctx->prof.size();
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = fl;
+    ctx->prof.clear();
+    return SL_OK;
+}
+
 int sl_malloc(sl_ctx* ctx, size_t bytes, void** out_dptr) {
     SL_REQUIRE(ctx, ctx && out_dptr, "NULL argument");
     *out_dptr = nullptr;

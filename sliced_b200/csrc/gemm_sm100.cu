@@ -146,9 +146,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 }
 
 // ------------------------------------------------------------------------------------------------ the MMA kernel
+//
+// Accumulation scheme ("promotion").  The tensor core adds each MMA's 8 products into the fp32 TMEM accumulator with
+// round-toward-zero, so a long K chain drifts linearly in K (measured: 13x the error of a CPU sgemm at K = 4096).
+// The kernel therefore never lets a TMEM chain run longer than `kc_blocks` k-blocks: the MMA warp ping-pongs between
+// two TMEM buffers, one K-chunk each, and the epilogue warps fold every finished chunk into per-thread fp32 REGISTER
+// accumulators with round-to-nearest adds (sqrt(K) growth, like a blocked CPU summation).  Folding a chunk (a
+// tcgen05.ld of the buffer + 128 FADDs per thread) overlaps the next chunk's MMAs, so it is free.
+// In TF32 fast mode the operand rounding dominates and kc_blocks is the whole K (single chunk).
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 8;  // 32 bytes of tf32 per MMA
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int GROUP_M = 8;
 
 struct GemmParams {
@@ -158,6 +167,7 @@ struct GemmParams {
     int accumulate;     // C += acc
     int relu;           // C = (v >= 0) * v after bias
     int c_vec_ok;       // N % 4 == 0 and C 16-byte aligned
+    int kc_blocks;      // k-blocks per TMEM accumulation chunk
 };
 
 template <int BLOCK_N, int BLOCK_K, int TERMS, int STAGES>
@@ -166,8 +176,9 @@ struct GemmCfg {
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
     static constexpr int PLANES = TERMS == 3 ? 2 : 1;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers; 256 or 512 (power of two)
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two chunk buffers; 256 or 512 (power of two)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int COLS_PER_WARP = BLOCK_N / (EPI_WARPS / 4);  // each lane quadrant is shared by EPI_WARPS/4 warps
     static_assert(SMEM_BYTES <= 227 * 1024, "stage ring does not fit in shared memory");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
 };
@@ -204,7 +215,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full_bar(s), 1);
-            mbar_init(tmem_empty_bar(s), 4);  // one arrival per epilogue warp
+            mbar_init(tmem_empty_bar(s), EPI_WARPS);  // one arrival per epilogue warp
         }
         fence_barrier_init();
         fence_proxy_async();
@@ -219,6 +230,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = num_m * num_n;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int kc = p.kc_blocks > 0 ? p.kc_blocks : num_kb;
+    const int num_chunks = (num_kb + kc - 1) / kc;
     auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
         const int group_size = GROUP_M * num_n;
         const int group = tile / group_size;
@@ -262,102 +275,117 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
-            int local = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-                const int acc = local & 1;
-                const uint32_t acc_phase = (local >> 1) & 1;
-                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator buffer
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+            uint32_t g = 0;  // global chunk counter: TMEM buffer = g & 1
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int ch = 0; ch < num_chunks; ++ch, ++g) {
+                    const uint32_t buf = g & 1;
+                    mbar_wait(tmem_empty_bar(buf), ((g >> 1) & 1) ^ 1);  // epilogue has folded this buffer's previous chunk
                     tc_fence_after();
-                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
-                    const uint64_t da_hi = make_smem_desc<BLOCK_K>(sa);
-                    const uint64_t db_hi = make_smem_desc<BLOCK_K>(sb);
-                    const uint64_t da_lo = make_smem_desc<BLOCK_K>(sa + Cfg::A_BYTES);
-                    const uint64_t db_lo = make_smem_desc<BLOCK_K>(sb + Cfg::B_BYTES);
+                    const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+                    const int kb_end = min(num_kb, (ch + 1) * kc);
+                    for (int kb = ch * kc; kb < kb_end; ++kb) {
+                        mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+                        const uint64_t da_hi = make_smem_desc<BLOCK_K>(sa);
+                        const uint64_t db_hi = make_smem_desc<BLOCK_K>(sb);
+                        const uint64_t da_lo = make_smem_desc<BLOCK_K>(sa + Cfg::A_BYTES);
+                        const uint64_t db_lo = make_smem_desc<BLOCK_K>(sb + Cfg::B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance the start address inside the swizzle atom
-                        const uint32_t first = (kb | k) == 0 ? 0u : 1u;
-                        if (TERMS == 3) {
-                            umma_tf32(tmem_d, da_lo + koff, db_hi + koff, idesc, first);
-                            umma_tf32(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
-                            umma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc, 1u);
-                        } else {
-                            umma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc, first);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);  // advance the start address inside the swizzle atom
+                            const uint32_t first = (kb == ch * kc && k == 0) ? 0u : 1u;
+                            if (TERMS == 3) {
+                                umma_tf32(tmem_d, da_lo + koff, db_hi + koff, idesc, first);
+                                umma_tf32(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                                umma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc, 1u);
+                            } else {
+                                umma_tf32(tmem_d, da_hi + koff, db_hi + koff, idesc, first);
+                            }
+                        }
+                        umma_commit(empty_bar(stage));  // stage is free once these MMAs have read it
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
                         }
                     }
-                    umma_commit(empty_bar(stage));  // stage is free once these MMAs have read it
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    umma_commit(tmem_full_bar(buf));  // chunk complete -> epilogue
                 }
-                umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
             }
         }
         __syncwarp();
     } else {
-        // ================================================================= epilogue (warps 2..5)
-        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
-        int local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        // ================================================================= epilogue (warps 2..9)
+        constexpr int CPW = Cfg::COLS_PER_WARP;
+        const int ew = warp - 2;
+        const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+        const int col0 = (ew >> 2) * CPW;     // this warp's column slice of the tile
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int m_blk, n_blk;
             tile_coords(tile, m_blk, n_blk);
-            const int acc = local & 1;
-            const uint32_t acc_phase = (local >> 1) & 1;
-            mbar_wait(tmem_full_bar(acc), acc_phase);
-            tc_fence_after();
-            const int row = m_blk * BLOCK_M + quad * 32 + lane;
-            const bool row_ok = row < p.M;
-            float* crow = p.C + (size_t)row * p.N;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32);
-                tmem_ld_32x32(taddr, r);
-                tmem_ld_wait();
-                const int n0 = n_blk * BLOCK_N + c * 32;
-                if (row_ok && n0 < p.N) {
-                    if (p.c_vec_ok && n0 + 32 <= p.N) {
+            float acc[CPW];
+            for (int ch = 0; ch < num_chunks; ++ch, ++g) {
+                const uint32_t buf = g & 1;
+                mbar_wait(tmem_full_bar(buf), (g >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                                   __uint_as_float(r[j + 3]));
-                            if (p.accumulate) {
-                                const float4 o = *reinterpret_cast<const float4*>(crow + n0 + j);
-                                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                            }
-                            if (p.bias) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                            }
-                            if (p.relu) {
-                                v.x = (v.x >= 0.f ? 1.f : 0.f) * v.x; v.y = (v.y >= 0.f ? 1.f : 0.f) * v.y;
-                                v.z = (v.z >= 0.f ? 1.f : 0.f) * v.z; v.w = (v.w >= 0.f ? 1.f : 0.f) * v.w;
-                            }
-                            *reinterpret_cast<float4*>(crow + n0 + j) = v;
-                        }
+                for (int c = 0; c < CPW / 32; ++c) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N + col0 + c * 32);
+                    tmem_ld_32x32(taddr, r);
+                    tmem_ld_wait();
+                    if (ch == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __uint_as_float(r[j]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (n0 + j < p.N) {
-                                float v = __uint_as_float(r[j]);
-                                if (p.accumulate) v += crow[n0 + j];
-                                if (p.bias) v += __ldg(p.bias + n0 + j);
+                        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);  // round-to-nearest promotion
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar(buf));
+            }
+            // ---- write the tile slice: optional += C, + bias, relu
+            const int row = m_blk * BLOCK_M + quad * 32 + lane;
+            if (row < p.M) {
+                float* crow = p.C + (size_t)row * p.N;
+                const int nbase = n_blk * BLOCK_N + col0;
+#pragma unroll
+                for (int j = 0; j < CPW; j += 4) {
+                    const int n0 = nbase + j;
+                    if (n0 >= p.N) break;
+                    if (p.c_vec_ok && n0 + 4 <= p.N) {
+                        float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                        if (p.accumulate) {
+                            const float4 o = *reinterpret_cast<const float4*>(crow + n0);
+                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                        }
+                        if (p.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        }
+                        if (p.relu) {
+                            v.x = (v.x >= 0.f ? 1.f : 0.f) * v.x; v.y = (v.y >= 0.f ? 1.f : 0.f) * v.y;
+                            v.z = (v.z >= 0.f ? 1.f : 0.f) * v.z; v.w = (v.w >= 0.f ? 1.f : 0.f) * v.w;
+                        }
+                        *reinterpret_cast<float4*>(crow + n0) = v;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (n0 + e < p.N) {
+                                float v = acc[j + e];
+                                if (p.accumulate) v += crow[n0 + e];
+                                if (p.bias) v += __ldg(p.bias + n0 + e);
                                 if (p.relu) v = (v >= 0.f ? 1.f : 0.f) * v;
-                                crow[n0 + j] = v;
+                                crow[n0 + e] = v;
                             }
                         }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
         }
     }
 
@@ -494,15 +522,22 @@ static int launch_cfg(sl_ctx* ctx, const GemmParams& p, const float* a_hi, const
         if ((rc = make_map(ctx, &mb_lo, b_lo, p.N, p.K, ldb, BLOCK_K, BLOCK_N)) != SL_OK) return rc;
     }
     auto kern = gemm_tf32_kernel<BLOCK_N, BLOCK_K, TERMS, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    SL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
     const int grid = num_tiles < ctx->num_sms ? num_tiles : ctx->num_sms;
+    sl_ctx::ProfRec rec{};
+    if (ctx->profiling) {
+        cudaEventCreate(&rec.a);
+        cudaEventCreate(&rec.b);
+        rec.flops = 2.0 * p.M * (double)p.N * p.K;
+        cudaEventRecord(rec.a, ctx->stream);
+    }
     kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
     ctx->launches++;
+    if (ctx->profiling) {
+        cudaEventRecord(rec.b, ctx->stream);
+        ctx->prof.push_back(rec);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return sl_set_error(ctx, SL_ERR_CUDA, "gemm_tf32_kernel launch: %s", cudaGetErrorString(e));
     return SL_OK;
@@ -523,6 +558,8 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const
     p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu;
     p.c_vec_ok = (N % 4 == 0) && sl_aligned16(C) && (!bias || sl_aligned16(bias));
     const bool three = a_lo != nullptr;
+    // K-chunk (in k-blocks of 32) accumulated inside TMEM before promotion to fp32 registers; 0 = whole K (TF32 fast mode)
+    p.kc_blocks = three ? env_int("SLICED_GEMM_KC", 4) : env_int("SLICED_GEMM_KC_TF32", 0);
     // tile configuration: SLICED_GEMM_CFG = 0 auto | 1: 128x256x32 | 2: 128x256x16 (swizzle 64B, deeper ring) | 3: 128x128x32
     int cfg = env_int("SLICED_GEMM_CFG", 0);
     if (cfg == 0) {

@@ -1,0 +1,108 @@
+// mlp.cpp — examples/nn.rs and examples/sine_net.rs training steps on the device (see mlp.hpp).
+#include "mlp.hpp"
+
+namespace slh {
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Mlp::Mlp(Device& dev, const std::vector<size_t>& dims, LossKind loss) : dev_(dev), dims_(dims), loss_(loss) {
+    if (dims.size() < 2) throw Error(SL_ERR_INVALID_ARG, "Mlp: need at least one layer");
+    // one flat parameter buffer and one flat gradient bucket; Linear's weights/bias (and their grads) are views into them
+    std::vector<size_t> off;
+    size_t total = 0;
+    for (size_t l = 0; l + 1 < dims.size(); ++l) {
+        off.push_back(total);
+        total += round_up(dims[l] * dims[l + 1], 64);
+        off.push_back(total);
+        total += round_up(dims[l + 1], 64);
+    }
+    n_params_ = total;
+    params_ = dev_.buffer(total, SL_F32);  // bias = zeros (Matrix::new, nn.rs:33); weights are written by the caller (rand, nn.rs:26)
+    bucket_ = dev_.buffer(total, SL_F32);
+    bucket_->requires_grad = false;
+    for (size_t l = 0; l + 1 < dims.size(); ++l) {
+        const size_t I = dims[l], O = dims[l + 1];
+        Buf w = dev_.wrap((float*)params_->dptr + off[2 * l], I * O, SL_F32);
+        Buf b = dev_.wrap((float*)params_->dptr + off[2 * l + 1], O, SL_F32);
+        Buf gw = dev_.wrap((float*)bucket_->dptr + off[2 * l], I * O, SL_F32);
+        Buf gb = dev_.wrap((float*)bucket_->dptr + off[2 * l + 1], O, SL_F32);
+        gw->requires_grad = gb->requires_grad = false;
+        dev_.bind_grad(w, gw);
+        dev_.bind_grad(b, gb);
+        layers_.push_back(Linear{Matrix(w, I, O), Matrix(b, 1, O)});
+    }
+    dev_.check(sl_malloc(dev_.ctx(), 16, &metrics_dev_));
+}
+
+Mlp::~Mlp() {
+    if (metrics_dev_) sl_free(dev_.ctx(), metrics_dev_);
+}
+
+StepResult Mlp::forward_backward(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics) {
+    Device& d = dev_;
+    const size_t L = layers_.size();
+    const size_t out_cols = dims_.back();
+    d.range_begin();   // `for epoch in device.range(..)` (nn.rs:184): rewind the Cached cursor
+    d.zero_grad();     // nn.rs:186-188
+    x->requires_grad = false;  // `.no_grad()` (nn.rs:170)
+    y->requires_grad = false;
+
+    Matrix out(x, batch, dims_[0]);
+    for (size_t l = 0; l < L; ++l) {                       // nn.rs:190-193
+        out = layers_[l].forward(out);
+        if (l + 1 < L) out = out.relu();
+        else if (loss_ == LOSS_SOFTMAX_CCE) out = out.softmax();
+    }
+    const size_t on = batch * out_cols;
+    d.check(sl_clear(d.ctx(), metrics_dev_, 16));
+    if (loss_ == LOSS_SOFTMAX_CCE) {
+        if (labels)  // accuracy: nn.rs:195-211 (a host loop in the reference; a kernel + one int here)
+            d.check(sl_count_correct(d.ctx(), SL_F32, batch, out_cols, out.data->dptr, (const int32_t*)labels->dptr, (int32_t*)metrics_dev_ + 1));
+        // cce(preds, targets, cols): nn.rs:124-138 — L2 ops, nothing goes on the tape
+        d.set_tape_enabled(false);
+        Buf preds = d.clip(out.data, 1E-7, 1. - 1E-7);
+        preds = d.binary_ew(SL_MUL, preds, y);
+        Buf per_sample = d.sum_cols(out_cols, preds);
+        Buf loss = d.apply_fn(per_sample, SL_UN_NEG_LN);
+        // cce_grad(preds, targets, rows): nn.rs:140-152
+        Buf grad = d.binary_ew(SL_DIV, y, out.data);
+        grad = d.apply_fn(grad, SL_UN_NEG_DIV_SCALAR, (double)grad_rows);
+        d.set_tape_enabled(true);
+        d.check(sl_sum(d.ctx(), SL_F32, loss->dptr, batch, metrics_dev_));   // device.mean(&loss) * batch (nn.rs:224)
+        d.backward_with(out.data, grad);                                      // nn.rs:233
+    } else {
+        Matrix ym(y, batch, out_cols);
+        Matrix loss = out.sub(ym).pow(2.);                                    // sine_net.rs:150
+        d.check(sl_sum(d.ctx(), SL_F32, loss.data->dptr, on, metrics_dev_));  // dev.mean(&loss) * len (sine_net.rs:151)
+        d.backward(loss.data);                                                // sine_net.rs:156
+    }
+    StepResult r;
+    if (want_metrics) {
+        struct { float loss; int32_t correct; } m;
+        d.check(sl_read(d.ctx(), &m, metrics_dev_, 8));  // the step's device -> host read
+        r.loss_sum = m.loss;
+        r.correct = m.correct;
+    }
+    return r;
+}
+
+void Mlp::allreduce_grads() { dev_.check(sl_allreduce_sum(dev_.ctx(), SL_F32, bucket_->dptr, n_params_)); }
+
+void Mlp::sgd(double lr) {
+    // SGD::step over lin1..lin3 params (nn.rs:235-237): parameters and gradients are both flat -> one kernel
+    dev_.check(sl_sgd_step(dev_.ctx(), SL_F32, params_->dptr, bucket_->dptr, lr, n_params_));
+}
+
+Matrix Mlp::predict(const Buf& x, size_t batch) {
+    dev_.set_tape_enabled(false);
+    Matrix out(x, batch, dims_[0]);
+    for (size_t l = 0; l < layers_.size(); ++l) {
+        out = layers_[l].forward(out);
+        if (l + 1 < layers_.size()) out = out.relu();
+        else if (loss_ == LOSS_SOFTMAX_CCE) out = out.softmax();
+    }
+    dev_.set_tape_enabled(true);
+    return out;
+}
+
+}  // namespace slh

@@ -1,0 +1,76 @@
+// mlp.hpp — the training loops of the reference's examples, on the device, written against slh::Device / slh::Matrix
+// exactly as the Rust examples are written against custos + sliced:
+//
+//   examples/nn.rs:13-54      Linear<I, O> { weights, bias }, forward = gemm + add_row_mut
+//   examples/nn.rs:86-119     SGD { lr }, step: w -= grad * lr
+//   examples/nn.rs:124-152    cce / cce_grad
+//   examples/nn.rs:184-237    one epoch: zero_grad -> 3 x (Linear, relu | softmax) -> accuracy -> loss -> backward_with -> sgd
+//   examples/sine_net.rs:135-163  the same with loss = (out - y)^2 and backward()
+//
+// Data-parallel extension (new functionality): every rank runs the step on its batch shard with
+// cce_grad scaled by the GLOBAL batch, the parameter gradients live in one flat bucket that is sum-all-reduced
+// (NCCL over NVLink) before the SGD step, so all replicas stay bit-identical.
+#pragma once
+
+#include <vector>
+
+#include "sliced_host.hpp"
+
+namespace slh {
+
+struct Linear {  // examples/nn.rs:13-16
+    Matrix weights;  // [I x O], require_grad
+    Matrix bias;     // [1 x O], require_grad
+    Matrix forward(const Matrix& inputs) const {  // examples/nn.rs:38-46
+        Matrix out = inputs.gemm(weights);
+        out.add_row_mut(bias);
+        return out;
+    }
+};
+
+enum LossKind { LOSS_SOFTMAX_CCE = 0 /* nn.rs */, LOSS_SQUARED = 1 /* sine_net.rs */ };
+
+struct StepResult {
+    double loss_sum = 0;   // sum over the local batch of the per-sample loss (mean = / batch)
+    long long correct = 0; // argmax == label count (nn.rs:195-211)
+};
+
+class Mlp {
+  public:
+    Mlp(Device& dev, const std::vector<size_t>& dims, LossKind loss);
+    ~Mlp();
+    Device& device() { return dev_; }
+    size_t n_layers() const { return layers_.size(); }
+    const std::vector<size_t>& dims() const { return dims_; }
+    Linear& layer(size_t l) { return layers_[l]; }
+    // all parameter gradients, contiguous: [W0 | b0 | W1 | b1 | ...] — the all-reduce bucket
+    Buf grad_bucket() { return bucket_; }
+    Buf params() { return params_; }
+    size_t n_params() const { return n_params_; }
+
+    // One training step, op by op like the reference.  x: [batch x dims[0]] (no_grad), y: [batch x dims.back()],
+    // labels: int32 [batch] or null.  grad_rows: the `rows` of cce_grad (nn.rs:151) — the global batch under DP.
+    // Phases can be run separately so that a data-parallel driver can put the exchange between backward and sgd.
+    StepResult forward_backward(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics);
+    void allreduce_grads();          // sl_allreduce_sum over the bucket (no-op for a world of one)
+    void sgd(double lr);             // SGD::step on every Linear (nn.rs:235-237)
+    StepResult step(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, double lr, bool want_metrics) {
+        StepResult r = forward_backward(x, y, labels, batch, grad_rows, want_metrics);
+        allreduce_grads();
+        sgd(lr);
+        return r;
+    }
+    Matrix predict(const Buf& x, size_t batch);  // forward only, tape disabled
+
+  private:
+    Device& dev_;
+    std::vector<size_t> dims_;
+    LossKind loss_;
+    std::vector<Linear> layers_;
+    Buf params_;
+    Buf bucket_;
+    size_t n_params_ = 0;
+    void* metrics_dev_ = nullptr;  // [loss_sum f32][correct i32]
+};
+
+}  // namespace slh

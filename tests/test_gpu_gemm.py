@@ -116,6 +116,23 @@ def test_tile_configs(cfg, mode):
         os.environ.pop("SLICED_GEMM_CFG", None)
 
 
+@pytest.mark.parametrize("kc", ["0", "1", "2", "8"])
+def test_promotion_chunk_lengths(kc, monkeypatch):
+    """SLICED_GEMM_KC: k-blocks per TMEM chunk before promotion to fp32 registers (0 = one chunk, no promotion).
+    Every setting is a correct gemm; shorter chunks are more accurate (round-to-nearest adds between chunks)."""
+    import sliced_b200 as S
+    monkeypatch.setenv("SLICED_GEMM_KC", kc)
+    ctx = S.Context(0)
+    for (m, n, k) in [(256, 512, 4096), (300, 700, 1000), (128, 256, 64)]:
+        rng = np.random.default_rng(k)
+        a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
+        t = truth(0, 0, m, n, k, a, b)
+        err = np.max(np.abs(run(ctx, 0, 0, m, n, k, a, b, S.GEMM_3XTF32) - t))
+        print(f"kc={kc} {m}x{n}x{k} err={err:.3e}")
+        assert err <= (4 * k * 2.0 ** -24 if kc != "0" else 16 * k * 2.0 ** -24), (kc, m, n, k, err)
+    ctx.close()
+
+
 def test_accumulate_and_set_semantics(ctx):
     """gemm is SET even into a junk-filled (Cached) buffer; accumulate=1 adds (the OpenCL reference's gemm_grad)"""
     import sliced_b200 as S
@@ -161,7 +178,7 @@ def test_3xtf32_is_fp32_class_on_ill_scaled_data(ctx):
     e3 = np.max(np.abs(run(ctx, 0, 0, m, n, k, a, b, S.GEMM_3XTF32) - t) / scale.ravel())
     e1 = np.max(np.abs(run(ctx, 0, 0, m, n, k, a, b, S.GEMM_TF32) - t) / scale.ravel())
     es = np.max(np.abs(O.gemm_ex(0, 0, m, n, k, a, b) - t) / scale.ravel())
-    assert e3 <= 2.0 ** -21, (e3, e1, es)
+    assert e3 <= 2 * es + 2.0 ** -23, (e3, e1, es)  # within 2x of the CPU sgemm's own error (componentwise relative)
     assert e1 > 16 * e3, "TF32 fast mode is not supposed to be this accurate: is the 3-term path really different?"
 
 

@@ -1,0 +1,105 @@
+"""
+The training loops of the reference's examples on the device (host layer `Mlp`) against the CPU oracle's op-by-op replay
+(oracle.mlp_step): examples/nn.rs (softmax + cce) and examples/sine_net.rs (squared error), same seeded init, several
+steps.  Tolerance: f32, relative 2e-5 on parameters after k steps (sums run in a different but deterministic order;
+large layers go through 3xTF32 tensor-core gemms, fp32-class).
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_problem(dims, batch, seed, classes=True):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, batch * dims[0]).astype(np.float32)
+    if classes:
+        labels = rng.integers(0, dims[-1], batch).astype(np.int32)
+        y = np.zeros((batch, dims[-1]), np.float32)
+        y[np.arange(batch), labels] = 1
+        y = y.ravel()
+    else:
+        labels = None
+        y = rng.uniform(-1, 1, batch * dims[-1]).astype(np.float32)
+    W = [rng.uniform(-0.1, 0.1, dims[i] * dims[i + 1]).astype(np.float32) for i in range(len(dims) - 1)]
+    B = [np.zeros(dims[i + 1], np.float32) for i in range(len(dims) - 1)]
+    return x, y, labels, W, B
+
+
+def run_gpu(dims, loss, x, y, labels, W, B, lr, steps, cached=True):
+    from sliced_b200.host import CUDA, Mlp
+    dev = CUDA(0, cached=cached)
+    mlp = Mlp(dev, dims, loss)
+    for l in range(len(dims) - 1):
+        mlp.weights(l).write(W[l])
+        mlp.bias(l).write(B[l])
+    batch = x.size // dims[0]
+    dx, dy = dev.buffer(x).no_grad(), dev.buffer(y).no_grad()
+    dl = dev.buffer(labels) if labels is not None else None
+    hist = []
+    for _ in range(steps):
+        hist.append(mlp.step(dx, dy, dl, batch, lr))
+    Wn = [mlp.weights(l).read() for l in range(len(dims) - 1)]
+    Bn = [mlp.bias(l).read() for l in range(len(dims) - 1)]
+    launches = dev.launches
+    del mlp, dx, dy, dl
+    dev.close()
+    return hist, Wn, Bn, launches
+
+
+@pytest.mark.parametrize("dims,batch", [([12, 16, 8, 10], 32), ([784, 128, 10, 10], 256), ([256, 512, 384, 10], 1024)])
+def test_nn_rs_step_matches_oracle(dims, batch):
+    x, y, labels, W, B = make_problem(dims, batch, 7)
+    Wo, Bo = [w.copy() for w in W], [b.copy() for b in B]
+    steps, lr = 3, 0.1
+    ref = [O.mlp_step(0, dims, x, y, labels, Wo, Bo, lr)[:2] for _ in range(steps)]
+    hist, Wn, Bn, _ = run_gpu(dims, 0, x, y, labels, W, B, lr, steps)
+    for (l_ref, c_ref), (l_gpu, c_gpu) in zip(ref, hist):
+        assert abs(l_gpu - l_ref) <= 2e-5 * abs(l_ref) + 1e-5, (l_gpu, l_ref)
+        assert c_gpu == c_ref
+    for a, b in zip(Wn + Bn, Wo + Bo):
+        assert np.max(np.abs(a - b)) <= 2e-5 * max(np.max(np.abs(b)), 1e-3), np.max(np.abs(a - b))
+
+
+def test_sine_net_matches_oracle():
+    """examples/sine_net.rs:119-166: x_i = i/1000, y = sin(2 pi x), 1-64-64-1, lr 1e-4 (shipped sizes), 50 steps"""
+    dims = [1, 64, 64, 1]
+    xs = (np.arange(1000) / 1000.0).astype(np.float32)
+    ys = np.sin(2.0 * xs * np.float32(np.pi)).astype(np.float32)
+    rng = np.random.default_rng(0)
+    W = [rng.uniform(-0.5, 0.5, dims[i] * dims[i + 1]).astype(np.float32) for i in range(3)]
+    B = [np.zeros(dims[i + 1], np.float32) for i in range(3)]
+    Wo, Bo = [w.copy() for w in W], [b.copy() for b in B]
+    steps, lr = 50, 1e-4
+    ref = [O.mlp_step(1, dims, xs, ys, None, Wo, Bo, lr)[0] for _ in range(steps)]
+    hist, Wn, Bn, launches = run_gpu(dims, 1, xs, ys, None, W, B, lr, steps)
+    for l_ref, (l_gpu, _) in zip(ref, hist):
+        assert abs(l_gpu - l_ref) <= 1e-4 * abs(l_ref), (l_gpu, l_ref)
+    assert ref[-1] < ref[0]
+    for a, b in zip(Wn + Bn, Wo + Bo):
+        assert np.max(np.abs(a - b)) <= 1e-4 * max(np.max(np.abs(b)), 1e-3)
+
+
+def test_dp_grad_scaling_equals_single_device():
+    """two half-batch shards with cce_grad scaled by the GLOBAL batch sum to the full-batch gradient"""
+    from sliced_b200.host import CUDA, Mlp
+    dims, batch = [64, 96, 10], 128
+    x, y, labels, W, B = make_problem(dims, batch, 3)
+    def grads(xs, ys, ls, rows):
+        dev = CUDA(0, cached=True)
+        mlp = Mlp(dev, dims, 0)
+        for l in range(2):
+            mlp.weights(l).write(W[l]); mlp.bias(l).write(B[l])
+        b = xs.size // dims[0]
+        mlp.forward_backward(dev.buffer(xs).no_grad(), dev.buffer(ys).no_grad(), dev.buffer(ls), b, rows)
+        g = mlp.grad_bucket().read()
+        del mlp
+        dev.close()
+        return g
+    full = grads(x, y, labels, batch)
+    h = batch // 2
+    a = grads(x[:h * 64], y[:h * 10], labels[:h], batch)
+    b = grads(x[h * 64:], y[h * 10:], labels[h:], batch)
+    assert np.max(np.abs((a + b) - full)) <= 1e-5 * np.max(np.abs(full))

@@ -131,7 +131,13 @@ def test_unary_libm(be, ob, dt, op):
     rel = 1e-6 if dt == "f32" else 1e-14
     close_rel(be.unary(op, x, p0), ob.unary(op, x, p0), rel, "fwd")
     z = np.zeros_like(x)
-    close_rel(be.unary_grad(op, x, z.copy(), og, p0), ob.unary_grad(op, x, z.copy(), og, p0), 2 * rel, "grad")
+    ga, gb = be.unary_grad(op, x, z.copy(), og, p0), ob.unary_grad(op, x, z.copy(), og, p0)
+    if op in (O.UN_TANH, O.UN_SIGMOID):
+        # 1 - tanh(x)^2 and e/(1+e)^2 cancel: a 1-ulp difference in tanhf/expf is amplified relative to a result << 1,
+        # so the derivative is held to 1e-6 of the function scale (|f'| <= 1), not of the (tiny) value
+        assert np.max(np.abs(ga.astype(np.float64) - gb.astype(np.float64))) <= (1e-6 if dt == "f32" else 1e-14)
+    else:
+        close_rel(ga, gb, 2 * rel, "grad")
     if op == O.UN_POW:  # the exponent sine_net uses, and a fractional one
         for p in (2.0, 0.5):
             close_rel(be.unary(op, x, p), ob.unary(op, x, p), rel, f"pow {p}")
