@@ -123,7 +123,11 @@ def make_host_problem(batch: int, seed: int = 7):
 
 def make_params(seed: int = 11):
     rng = np.random.default_rng(seed)
-    W = [rng.uniform(-0.1, 0.1, DIMS[i] * DIMS[i + 1]).astype(np.float32) for i in range(len(DIMS) - 1)]   # nn.rs:26
+    # nn.rs:26 draws U(-0.1, 0.1); at width 4096 that saturates the softmax in the first forward pass and the reference's own
+    # cce_grad (targets / preds, nn.rs:150) then divides 0 by 0.  The bound is therefore capped at the Xavier limit so that the
+    # synthetic run trains (finite loss); shapes, op sequence and cost are unchanged.
+    W = [rng.uniform(-1, 1, DIMS[i] * DIMS[i + 1]).astype(np.float32) * np.float32(min(0.1, (6.0 / (DIMS[i] + DIMS[i + 1])) ** 0.5))
+         for i in range(len(DIMS) - 1)]
     B = [np.zeros(DIMS[i + 1], np.float32) for i in range(len(DIMS) - 1)]                                   # nn.rs:33
     return W, B
 
@@ -237,7 +241,8 @@ def run_ours(args):
         return mlp.step(bx, by, bl, batch, LR, grad_rows=global_batch, want_metrics=metrics)
 
     # ---------------- device-resident leg (`value`)
-    for _ in range(max(args.warmup, 3)):
+    first_metrics = resident_step(True)
+    for _ in range(max(args.warmup, 3) - 1):
         resident_step(True)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -260,25 +265,39 @@ def run_ours(args):
     ms_step = max_over_ranks(ms_total / args.steps)
     value = global_batch / (ms_step * 1e-3)
     loss_sum, correct = resident_step(True)
+    first_loss = first_metrics[0] / batch
 
     # ---------------- end-to-end leg: host buffers in, loss/accuracy out, every step
-    xs, ys, ls = dev.zeros(batch * DIMS[0]), dev.zeros(batch * DIMS[-1]), dev.zeros(batch, np.int32)
-    xs.no_grad(); ys.no_grad()
+    # two staging sets: batch i+1 uploads on the copy stream (sl_write_prefetch) while step i computes; every step's inputs are
+    # copied exactly once, inside the timed region, and every step's loss / accuracy is read back (a blocking 8-byte read)
+    stage = []
+    for _ in range(2):
+        sx, sy, sl_ = dev.zeros(batch * DIMS[0]), dev.zeros(batch * DIMS[-1]), dev.zeros(batch, np.int32)
+        sx.no_grad(); sy.no_grad()
+        stage.append((sx, sy, sl_))
     h2d = x_pin.numel() * 4 + y_pin.numel() * 4 + l_pin.numel() * 4
     d2h = 8
 
-    def e2e_step():
-        capi.check(ctx, lib.sl_write(ctx, xs.ptr, x_pin.data_ptr(), x_pin.numel() * 4))
-        capi.check(ctx, lib.sl_write(ctx, ys.ptr, y_pin.data_ptr(), y_pin.numel() * 4))
-        capi.check(ctx, lib.sl_write(ctx, ls.ptr, l_pin.data_ptr(), l_pin.numel() * 4))
-        return mlp.step(xs, ys, ls, batch, LR, grad_rows=global_batch, want_metrics=True)
+    def upload(slot):
+        sx, sy, sl_ = stage[slot]
+        capi.check(ctx, lib.sl_prefetch_release(ctx))   # the copy may not overtake compute that still reads this slot
+        capi.check(ctx, lib.sl_write_prefetch(ctx, sx.ptr, x_pin.data_ptr(), x_pin.numel() * 4))
+        capi.check(ctx, lib.sl_write_prefetch(ctx, sy.ptr, y_pin.data_ptr(), y_pin.numel() * 4))
+        capi.check(ctx, lib.sl_write_prefetch(ctx, sl_.ptr, l_pin.data_ptr(), l_pin.numel() * 4))
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(nsteps):
+        upload(0)
+        for i in range(nsteps):
+            capi.check(ctx, lib.sl_prefetch_wait(ctx))  # compute stream waits for batch i
+            if i + 1 < nsteps:
+                upload((i + 1) & 1)                     # batch i+1 goes up while step i runs
+            sx, sy, sl_ = stage[i & 1]
+            mlp.step(sx, sy, sl_, batch, LR, grad_rows=global_batch, want_metrics=True)
+
+    e2e_run(2)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
@@ -303,7 +322,8 @@ def run_ours(args):
                                 gemm_mode=args.gemm_mode, l2="inputs (>= 128 MiB per operand at every N) exceed the 126 MB L2; no flush needed"),
                     e2e=dict(value=global_batch / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline,
-                    last_step=dict(mean_loss=loss_sum / batch, accuracy=correct / batch))
+                    training=dict(first_step_mean_loss=first_loss, last_step_mean_loss=loss_sum / batch, last_step_accuracy=correct / batch,
+                                  init="W ~ U(-a, a), a = min(0.1, sqrt(6/(fan_in+fan_out))); b = 0"))
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_rate(1, 0, args.cpu_sample)
             line["cpu_baseline"] = cb

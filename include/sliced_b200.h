@@ -125,6 +125,13 @@ int sl_host_alloc(sl_ctx* ctx, size_t bytes, void** out_hptr);
 int sl_host_free(sl_ctx* ctx, void* hptr);
 /* ref: custos `WriteBuf::write` † — host -> device, async on the ctx stream */
 int sl_write(sl_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+/* Upload pipeline for a training loop that streams batches from (pinned) host memory: sl_write_prefetch copies on the context's
+ * second (copy) stream so the next batch uploads while the current step computes; sl_prefetch_wait makes the compute stream wait for
+ * every prefetch issued so far; sl_prefetch_release makes the copy stream wait for the compute issued so far (call it before
+ * overwriting a staging buffer that earlier compute may still read). */
+int sl_write_prefetch(sl_ctx* ctx, void* dst_dev, const void* src_host_pinned, size_t bytes);
+int sl_prefetch_wait(sl_ctx* ctx);
+int sl_prefetch_release(sl_ctx* ctx);
 /* ref: custos `Read::read` † — device -> host, blocks until the data is on the host */
 int sl_read(sl_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 /* ref: custos `CloneBuf` / `WriteBuf::write_buf` † — device -> device */

@@ -28,6 +28,9 @@ struct sl_ctx {
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; double flops; };
     std::vector<ProfRec> prof;
+    // second stream for host->device prefetch (sl_write_prefetch), created lazily
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done = nullptr, compute_done = nullptr;
     // NCCL (dlopen'ed lazily)
     void* nccl_comm = nullptr;
     int nranks = 1;

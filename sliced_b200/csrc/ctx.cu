@@ -105,6 +105,12 @@ int sl_ctx_destroy(sl_ctx* ctx) {
     sl_comm_destroy(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ws2) cudaFree(ctx->ws2);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        cudaEventDestroy(ctx->copy_done);
+        cudaEventDestroy(ctx->compute_done);
+    }
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SL_OK;
@@ -184,6 +190,42 @@ int sl_write(sl_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
     if (bytes == 0) return SL_OK;
     SL_REQUIRE(ctx, dst_dev && src_host, "NULL pointer");
     SL_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SL_OK;
+}
+
+static int ensure_copy_stream(sl_ctx* ctx) {
+    if (!ctx->copy_stream) {
+        SL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        SL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+        SL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->compute_done, cudaEventDisableTiming));
+    }
+    return SL_OK;
+}
+
+int sl_write_prefetch(sl_ctx* ctx, void* dst_dev, const void* src_host_pinned, size_t bytes) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (bytes == 0) return SL_OK;
+    SL_REQUIRE(ctx, dst_dev && src_host_pinned, "NULL pointer");
+    int rc = ensure_copy_stream(ctx);
+    if (rc != SL_OK) return rc;
+    SL_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host_pinned, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    return SL_OK;
+}
+
+int sl_prefetch_wait(sl_ctx* ctx) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (!ctx->copy_stream) return SL_OK;
+    SL_CUDA(ctx, cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    SL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+    return SL_OK;
+}
+
+int sl_prefetch_release(sl_ctx* ctx) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    int rc = ensure_copy_stream(ctx);
+    if (rc != SL_OK) return rc;
+    SL_CUDA(ctx, cudaEventRecord(ctx->compute_done, ctx->stream));
+    SL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->compute_done, 0));
     return SL_OK;
 }
 

@@ -27,6 +27,8 @@
 
 int sl_gemm_simt(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
                  int accumulate);
+int sl_gemm_skinny_f32(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const float* a, const float* b, float* c,
+                       int accumulate);
 
 namespace {
 
@@ -611,6 +613,10 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
     if (mode < 0) mode = ctx->gemm_mode;
     if (dtype != SL_F32 || mode == SL_GEMM_SIMT || !tc_eligible(m, n, k)) {
         if (bias || relu) return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "fused epilogue needs the tensor-core path");
+        if (dtype == SL_F32 && mode != SL_GEMM_SIMT) {  // HBM-bound skinny shapes (n <= 16 or k <= 16) have their own kernels
+            int rc = sl_gemm_skinny_f32(ctx, trans_a, trans_b, m, n, k, (const float*)a, (const float*)b, (float*)c, accumulate);
+            if (rc <= 0) return rc;
+        }
         return sl_gemm_simt(ctx, dtype, trans_a, trans_b, m, n, k, a, b, c, accumulate);
     }
     const bool three = mode == SL_GEMM_3XTF32;

@@ -200,3 +200,27 @@ def test_full_size_sampled(ctx, mode):
     # linearity: (2A)B == 2(AB) exactly (power-of-two scaling commutes with every rounding step)
     c2 = ctx.gemm(m, k, n, ctx.array(a * 2), db, mode=md).numpy().reshape(m, n)
     assert np.array_equal(c2[rows], 2 * c[rows])
+
+
+@pytest.mark.parametrize("case", [("NN", 0, 0, 1000, 10, 4096), ("NN", 0, 0, 257, 16, 300), ("NN", 0, 0, 4096, 1, 1000),
+                                  ("TN", 1, 0, 512, 10, 8192), ("TN", 1, 0, 1030, 7, 5000), ("TN", 1, 0, 4096, 10, 2048),
+                                  ("NT", 0, 1, 1000, 512, 10), ("NT", 0, 1, 333, 1026, 16), ("NT", 0, 1, 64, 64, 3)],
+                         ids=lambda c: f"{c[0]}-{c[3]}x{c[4]}x{c[5]}")
+def test_skinny_shapes(case, monkeypatch):
+    """the HBM-bound skinny kernels (the 10-class head of the nn.rs MLP): fp32 FMA accumulation, K-scaled tolerance"""
+    import sliced_b200 as S
+    monkeypatch.delenv("SLICED_GEMM_TC_FORCE", raising=False)   # default dispatch: these shapes never reach the tensor cores
+    ctx = S.Context(0)
+    _, ta, tb, m, n, k = case
+    rng = np.random.default_rng(m + n + k)
+    a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
+    c0 = rng.uniform(-1, 1, m * n).astype(np.float32)
+    t = truth(ta, tb, m, n, k, a, b)
+    tol = 4 * k * 2.0 ** -24
+    got = run(ctx, ta, tb, m, n, k, a, b, S.GEMM_3XTF32)
+    assert np.max(np.abs(got - t)) <= tol
+    got = run(ctx, ta, tb, m, n, k, a, b, S.GEMM_3XTF32, c0, True)
+    assert np.max(np.abs(got - (t + c0))) <= tol + 2.0 ** -22
+    exact = run(ctx, ta, tb, m, n, k, a, b, S.GEMM_SIMT)          # SIMT mode stays bit-identical to the oracle
+    assert np.array_equal(exact, O.gemm_ex(ta, tb, m, n, k, a, b))
+    ctx.close()
