@@ -151,7 +151,12 @@ template <int OP, typename T>
 __device__ __forceinline__ T unary_f(T x, T p0, T p1) {
     switch (OP) {
     case SL_UN_SQUARE: return x * x;
-    case SL_UN_POW: return m_pow(x, p0);
+    case SL_UN_POW:
+        // small integer exponents (sine_net's pow(2.), tests' pow(3.)) as products: <= 1.5 ulp from the exact power, inside
+        // the 1e-6 tolerance, and the op stays HBM-bound instead of powf-bound (warp-uniform branch on the scalar p0)
+        if (p0 == T(2)) return x * x;
+        if (p0 == T(3)) return x * x * x;
+        return m_pow(x, p0);
     case SL_UN_RELU: return T(x >= T(0) ? 1 : 0) * x;
     case SL_UN_TANH: return m_tanh(x);
     case SL_UN_SIGMOID: return T(1) / (T(1) + m_exp(-x));
@@ -170,7 +175,10 @@ template <int OP, typename T>
 __device__ __forceinline__ T unary_d(T x, T p0, T p1) {
     switch (OP) {
     case SL_UN_SQUARE: return x * T(2);
-    case SL_UN_POW: return m_pow(x, p0 - T(1)) * p0;
+    case SL_UN_POW:
+        if (p0 == T(2)) return x * p0;          // x^(2-1) * 2
+        if (p0 == T(3)) return (x * x) * p0;    // x^(3-1) * 3
+        return m_pow(x, p0 - T(1)) * p0;
     case SL_UN_RELU: return T(x >= T(0) ? 1 : 0);
     case SL_UN_TANH: { T t = m_tanh(x); return T(1) - t * t; }
     case SL_UN_SIGMOID: { T e = m_exp(-x); T d = T(1) + e; return e / (d * d); }

@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(256) rowreduce_kernel(size_t rows, size_t cols
 // max_cols_grad: first c with x[r,c] == out[r] gets += og[r]
 template <typename T, int TPR>
 __global__ void __launch_bounds__(256) max_cols_grad_kernel(size_t rows, size_t cols, const T* __restrict__ out, const T* __restrict__ x,
-                                                            T* xg, const T* __restrict__ og) {
+                                                            T* xg, const T* __restrict__ og, bool vec) {
     constexpr int ROWS_PER_BLOCK = 256 / TPR;
     __shared__ int32_t s_idx[8];
     const int lane = threadIdx.x % TPR;
@@ -544,10 +544,33 @@ __global__ void __launch_bounds__(256) max_cols_grad_kernel(size_t rows, size_t 
         if (active) {
             const T mx = __ldg(out + r);
             const T* row = x + r * cols;
-            for (size_t c = lane; c < cols; c += TPR) {
-                if (__ldg(row + c) == mx) {
-                    ai = (int32_t)c;
-                    break;  // this thread's columns are visited in increasing order
+            if (vec) {
+                // whole row in 128-bit packs, 4 packs in flight per thread (no early exit: the row is read exactly once, 4 B/elem)
+                constexpr int V = Pack<T>::N;
+                const size_t colpacks = cols / V;
+                for (size_t cp0 = lane; cp0 < colpacks; cp0 += (size_t)TPR * RB) {
+                    Pack<T> a[RB];
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        const size_t cp = cp0 + (size_t)j * TPR;
+                        if (cp < colpacks) a[j] = ld_stream(row + cp * V);
+                    }
+#pragma unroll
+                    for (int j = 0; j < RB; ++j) {
+                        const size_t cp = cp0 + (size_t)j * TPR;
+                        if (cp < colpacks) {
+#pragma unroll
+                            for (int e = V - 1; e >= 0; --e)
+                                if (a[j].v[e] == mx && (int32_t)(cp * V + e) < ai) ai = (int32_t)(cp * V + e);
+                        }
+                    }
+                }
+            } else {
+                for (size_t c = lane; c < cols; c += TPR) {
+                    if (__ldg(row + c) == mx) {
+                        ai = (int32_t)c;
+                        break;  // this thread's columns are visited in increasing order
+                    }
                 }
             }
         }
@@ -962,8 +985,9 @@ int sl_max_cols_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const voi
     SL_REQUIRE(ctx, out && x && x_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
         const unsigned grid = tpr_grid(ctx, rows, cols);
+        const bool vec = cols >= 64 && cols % Pack<T>::N == 0 && sl_aligned16(x);
         SL_TPR_SWITCH(cols, TPRV, SL_LAUNCH(ctx, (max_cols_grad_kernel<T, TPRV>), grid, 256, 0, rows, cols, (const T*)out, (const T*)x,
-                                            (T*)x_grad, (const T*)out_grad));
+                                            (T*)x_grad, (const T*)out_grad, vec));
     });
     return SL_OK;
 }

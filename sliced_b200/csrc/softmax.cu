@@ -265,8 +265,10 @@ struct BlockPlan {
 template <typename T>
 static BlockPlan plan_block(size_t features, int max_np) {
     const size_t packs = features / Pack<T>::N;
-    for (int np = 1; np <= max_np; np *= 2)
-        for (int th = 256; th <= 1024; th *= 2)
+    // smallest block first: several resident blocks per SM sit in different phases (load / reduce / exp / store), which keeps HBM
+    // busy while one block is inside its reductions (one 1024-thread block per SM measured 54 % of peak at 16384 features)
+    for (int th = 256; th <= 1024; th *= 2)
+        for (int np = 1; np <= max_np; np *= 2)
             if ((size_t)np * th >= packs) return {th, np};
     return {0, 0};
 }

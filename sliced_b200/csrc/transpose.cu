@@ -49,6 +49,54 @@ __global__ void __launch_bounds__(256) transpose_kernel(size_t rows, size_t cols
     }
 }
 
+// 128-bit variant: rows and cols multiples of VEC, 16-byte aligned pointers.  Loads and stores are both LDG/STG.128 on
+// contiguous row segments; the 64x64 tile lives in padded shared memory and is read back column-wise (4 scalar LDS per
+// 128-bit store).  Same arithmetic-free data movement => bit-exact.
+template <typename T, bool ACC>
+__global__ void __launch_bounds__(256) transpose_vec_kernel(size_t rows, size_t cols, const T* __restrict__ x, T* out) {
+    constexpr int V = Pack<T>::N;
+    constexpr int PR = TT / V;              // packs per tile row
+    constexpr int RP = 256 / PR;            // tile rows covered per pass
+    __shared__ T tile[TT][TT + 1];
+    const size_t tiles_c = (cols + TT - 1) / TT;
+    const size_t tiles_r = (rows + TT - 1) / TT;
+    const size_t ntiles = tiles_c * tiles_r;
+    const int t = threadIdx.y * 32 + threadIdx.x;
+    const int pk = t % PR, rr = t / PR;
+    for (size_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const size_t r0 = (tix / tiles_c) * TT, c0 = (tix % tiles_c) * TT;
+#pragma unroll
+        for (int i = 0; i < TT; i += RP) {
+            const size_t r = r0 + rr + i, c = c0 + (size_t)pk * V;
+            if (r < rows && c < cols) {
+                const Pack<T> v = ld_stream(x + r * cols + c);
+#pragma unroll
+                for (int e = 0; e < V; ++e) tile[rr + i][pk * V + e] = v.v[e];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < TT; i += RP) {
+            const size_t c = c0 + rr + i, r = r0 + (size_t)pk * V;   // output row = input column c; V consecutive input rows
+            if (c < cols && r < rows) {
+                Pack<T> v;
+#pragma unroll
+                for (int e = 0; e < V; ++e) v.v[e] = tile[pk * V + e][rr + i];
+                T* dst = out + c * rows + r;
+                if (ACC) {
+                    const Pack<T> o = ld_pack(dst);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) v.v[e] += o.v[e];
+                    st_pack(dst, v);
+                } else {
+                    st_stream(dst, v);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T>
 __global__ void diagflat_kernel(size_t n, const T* __restrict__ x, T* __restrict__ out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i * n + i] = x[i];
@@ -108,8 +156,14 @@ int sl_transpose(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x
     const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
     const dim3 block(32, TROWS, 1);
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
-        if (accumulate) SL_LAUNCH(ctx, (transpose_kernel<T, true>), grid, block, 0, rows, cols, (const T*)x, (T*)out);
-        else SL_LAUNCH(ctx, (transpose_kernel<T, false>), grid, block, 0, rows, cols, (const T*)x, (T*)out);
+        const bool vec = rows % Pack<T>::N == 0 && cols % Pack<T>::N == 0 && sl_aligned16(x) && sl_aligned16(out);
+        if (vec) {
+            if (accumulate) SL_LAUNCH(ctx, (transpose_vec_kernel<T, true>), grid, block, 0, rows, cols, (const T*)x, (T*)out);
+            else SL_LAUNCH(ctx, (transpose_vec_kernel<T, false>), grid, block, 0, rows, cols, (const T*)x, (T*)out);
+        } else {
+            if (accumulate) SL_LAUNCH(ctx, (transpose_kernel<T, true>), grid, block, 0, rows, cols, (const T*)x, (T*)out);
+            else SL_LAUNCH(ctx, (transpose_kernel<T, false>), grid, block, 0, rows, cols, (const T*)x, (T*)out);
+        }
     });
     return SL_OK;
 }
