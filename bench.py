@@ -215,6 +215,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     mlp = Mlp(dev, DIMS, 0)
+    mlp.set_fused(not args.unfused)
     W, B = make_params()  # identical seeded init on every rank (replicas stay bit-identical: same summed gradients)
     for l in range(len(DIMS) - 1):
         mlp.weights(l).write(W[l])
@@ -319,7 +320,7 @@ def run_ours(args):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
                     higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=WORKLOAD, global_batch=global_batch, per_gpu_batch=batch, parallelism=f"dp{world}",
-                                gemm_mode=args.gemm_mode, l2="inputs (>= 128 MiB per operand at every N) exceed the 126 MB L2; no flush needed"),
+                                gemm_mode=args.gemm_mode, fused_epilogues=not args.unfused, l2="inputs (>= 128 MiB per operand at every N) exceed the 126 MB L2; no flush needed"),
                     e2e=dict(value=global_batch / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline,
                     training=dict(first_step_mean_loss=first_loss, last_step_mean_loss=loss_sum / batch, last_step_accuracy=correct / batch,
@@ -344,6 +345,7 @@ def main():
     ap.add_argument("--gemm-mode", choices=["3xtf32", "tf32"], default="3xtf32")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="run the op-by-op tape instead of the fused-epilogue step (bit-identical results)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

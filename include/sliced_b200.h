@@ -213,6 +213,17 @@ int sl_gemm_ex(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_
 int sl_gemm_grad(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs,
                  void* lhs_grad, void* rhs_grad, const void* out_grad, int accumulate, int mode);
 
+/* Fused Linear forward — examples/nn.rs:38-46 (`gemm` + `add_row_mut`) followed by `Matrix::relu` (src/matrix.rs:169-190) in the gemm
+ * epilogue:  z[m x n] = lhs[m x k] * rhs[k x n] + bias[n];  if act_out != NULL: act_out = (z >= 0) * z.   bias may be NULL.
+ * Bit-identical to sl_gemm + sl_add_row_mut + sl_unary(SL_UN_RELU): the same per-element operations in the same order. f32. */
+int sl_linear_fwd(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, const void* bias, void* z_out,
+                  void* act_out, int mode);
+/* Fused input-gradient of a Linear whose input came out of a relu:
+ *   x_grad[m x k] = (z_prev[m x k] >= 0) * (out_grad[m x n] * rhs[k x n]^T)        (SET)
+ * == sl_gemm_grad(lhs_grad only) followed by sl_unary_grad(SL_UN_RELU) into a zeroed gradient (ops.rs:260-275, matrix.rs:183-188). f32. */
+int sl_linear_bwd_input_relu(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* rhs, const void* out_grad, const void* z_prev,
+                             void* x_grad, int mode);
+
 /* ---------------------------------------------------------------- R: reductions */
 
 /* Scalar reductions; result is written to a device scalar `out_dev` (1 element of dtype).

@@ -170,7 +170,45 @@ struct GemmParams {
     int relu;           // C = (v >= 0) * v after bias
     int c_vec_ok;       // N % 4 == 0 and C 16-byte aligned
     int kc_blocks;      // k-blocks per TMEM accumulation chunk
+    float* C2;              // optional second output: C2 = (v >= 0) * v of the value stored to C (fused Matrix::relu)
+    const float* mask_src;  // optional [M x N]: v *= (mask_src >= 0) before the store (fused relu gradient)
 };
+
+// shared epilogue arithmetic of both MMA kernels: 4 consecutive columns of one output row
+__device__ __forceinline__ void epilogue_store4(const GemmParams& p, float* crow, size_t row_off, int n0, float4 v) {
+    if (p.accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(crow + n0);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    if (p.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (p.mask_src) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(p.mask_src + row_off + n0));
+        v.x = (m.x >= 0.f ? 1.f : 0.f) * v.x; v.y = (m.y >= 0.f ? 1.f : 0.f) * v.y;
+        v.z = (m.z >= 0.f ? 1.f : 0.f) * v.z; v.w = (m.w >= 0.f ? 1.f : 0.f) * v.w;
+    }
+    if (p.relu) {
+        v.x = (v.x >= 0.f ? 1.f : 0.f) * v.x; v.y = (v.y >= 0.f ? 1.f : 0.f) * v.y;
+        v.z = (v.z >= 0.f ? 1.f : 0.f) * v.z; v.w = (v.w >= 0.f ? 1.f : 0.f) * v.w;
+    }
+    *reinterpret_cast<float4*>(crow + n0) = v;
+    if (p.C2) {
+        float4 r;
+        r.x = (v.x >= 0.f ? 1.f : 0.f) * v.x; r.y = (v.y >= 0.f ? 1.f : 0.f) * v.y;
+        r.z = (v.z >= 0.f ? 1.f : 0.f) * v.z; r.w = (v.w >= 0.f ? 1.f : 0.f) * v.w;
+        *reinterpret_cast<float4*>(p.C2 + row_off + n0) = r;
+    }
+}
+__device__ __forceinline__ void epilogue_store1(const GemmParams& p, float* crow, size_t row_off, int n, float v) {
+    if (p.accumulate) v += crow[n];
+    if (p.bias) v += __ldg(p.bias + n);
+    if (p.mask_src) v = (__ldg(p.mask_src + row_off + n) >= 0.f ? 1.f : 0.f) * v;
+    if (p.relu) v = (v >= 0.f ? 1.f : 0.f) * v;
+    crow[n] = v;
+    if (p.C2) p.C2[row_off + n] = (v >= 0.f ? 1.f : 0.f) * v;
+}
 
 template <int BLOCK_N, int BLOCK_K, int TERMS, int STAGES>
 struct GemmCfg {
@@ -360,31 +398,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     const int n0 = nbase + j;
                     if (n0 >= p.N) break;
                     if (p.c_vec_ok && n0 + 4 <= p.N) {
-                        float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                        if (p.accumulate) {
-                            const float4 o = *reinterpret_cast<const float4*>(crow + n0);
-                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                        }
-                        if (p.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
-                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                        }
-                        if (p.relu) {
-                            v.x = (v.x >= 0.f ? 1.f : 0.f) * v.x; v.y = (v.y >= 0.f ? 1.f : 0.f) * v.y;
-                            v.z = (v.z >= 0.f ? 1.f : 0.f) * v.z; v.w = (v.w >= 0.f ? 1.f : 0.f) * v.w;
-                        }
-                        *reinterpret_cast<float4*>(crow + n0) = v;
+                        epilogue_store4(p, crow, (size_t)row * p.N, n0, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (n0 + e < p.N) {
-                                float v = acc[j + e];
-                                if (p.accumulate) v += crow[n0 + e];
-                                if (p.bias) v += __ldg(p.bias + n0 + e);
-                                if (p.relu) v = (v >= 0.f ? 1.f : 0.f) * v;
-                                crow[n0 + e] = v;
-                            }
-                        }
+                        for (int e = 0; e < 4; ++e)
+                            if (n0 + e < p.N) epilogue_store1(p, crow, (size_t)row * p.N, n0 + e, acc[j + e]);
                     }
                 }
             }
@@ -396,6 +414,279 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the 2-CTA MMA kernel
+//
+// cta_group::2: two CTAs on the SMs of one TPC (a cluster of 2) compute one 256 x 256 tile.  Each CTA stages ITS 128 rows
+// of A and ITS 128 rows (N) of B; the leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256),
+// which reads both CTAs' shared memory and writes each CTA's 128 accumulator rows into that CTA's own TMEM.
+// Per CTA and k-block this moves 64 KB (3xTF32) from L2 instead of the 96 KB of the 128 x 256 single-CTA tile: the
+// single-CTA kernel is bound by L2 -> SM traffic (ncu: 12.3 TB/s of xbar reads at 77 % tensor-pipe activity).
+//   full[s]        lives in the leader; both CTAs' TMA loads complete_tx on it (cp.async.bulk.tensor .cta_group::2)
+//   empty[s]       one per CTA, released by the leader's tcgen05.commit multicast to both CTAs
+//   tmem_full[b]   one per CTA (multicast commit);   tmem_empty[b] in the leader, 2 x 8 epilogue-warp arrivals (remote via mapa)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose mbarrier may live in the peer CTA of the pair (the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_leader, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_leader), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once the issued MMAs retire) on the barrier at the same shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+
+template <int TERMS, int STAGES>
+struct Gemm2Cfg {
+    static constexpr int BLOCK_K = 32;
+    static constexpr int TILE_M = 256, TILE_N = 256;       // per CTA pair
+    static constexpr int A_BYTES = 128 * BLOCK_K * 4;      // this CTA's 128 rows of A
+    static constexpr int B_BYTES = 128 * BLOCK_K * 4;      // this CTA's 128 rows (N) of B
+    static constexpr int PLANES = TERMS == 3 ? 2 : 1;
+    static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+    static constexpr int TMEM_COLS = 2 * TILE_N;           // two chunk buffers of 256 fp32 columns
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int COLS_PER_WARP = TILE_N / (EPI_WARPS / 4);
+    static_assert(SMEM_BYTES <= 227 * 1024, "stage ring does not fit in shared memory");
+};
+
+template <int TERMS, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
+    using Cfg = Gemm2Cfg<TERMS, STAGES>;
+    constexpr int BLOCK_K = Cfg::BLOCK_K;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_b_hi);
+        if (TERMS == 3) {
+            tma_prefetch_desc(&map_a_lo);
+            tma_prefetch_desc(&map_b_lo);
+        }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);     // leader's producer arrives (+ both CTAs' transaction bytes); unused in the peer
+            mbar_init(empty_bar(s), 1);    // one multicast commit
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tmem_full_bar(s), 1);
+            mbar_init(tmem_empty_bar(s), 2 * EPI_WARPS);  // both CTAs' epilogue warps; only the leader's copy is used
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // barriers of both CTAs are initialised before anything remote touches them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int num_m = (p.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+    const int num_n = (p.N + Cfg::TILE_N - 1) / Cfg::TILE_N;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int kc = p.kc_blocks > 0 ? p.kc_blocks : num_kb;
+    const int num_chunks = (num_kb + kc - 1) / kc;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+        const int group_size = GROUP_M * num_n;
+        const int group = tile / group_size;
+        const int first_m = group * GROUP_M;
+        const int gsz = min(num_m - first_m, GROUP_M);
+        const int in_group = tile - group * group_size;
+        m_blk = first_m + in_group % gsz;
+        n_blk = in_group / gsz;
+    };
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                int m_blk, n_blk;
+                tile_coords(tile, m_blk, n_blk);
+                const int row_a = m_blk * Cfg::TILE_M + (int)rank * 128;
+                const int row_b = n_blk * Cfg::TILE_N + (int)rank * 128;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+                    const uint32_t fb = mapa_shared(full_bar(stage), 0);  // the leader's barrier, as a shared::cluster address
+                    if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+                    tma_load_2d_2sm(sa, &map_a_hi, fb, kb * BLOCK_K, row_a);
+                    tma_load_2d_2sm(sb, &map_b_hi, fb, kb * BLOCK_K, row_b);
+                    if (TERMS == 3) {
+                        tma_load_2d_2sm(sa + Cfg::A_BYTES, &map_a_lo, fb, kb * BLOCK_K, row_a);
+                        tma_load_2d_2sm(sb + Cfg::B_BYTES, &map_b_lo, fb, kb * BLOCK_K, row_b);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (leader CTA only)
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(Cfg::TILE_M, Cfg::TILE_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t g = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                for (int ch = 0; ch < num_chunks; ++ch, ++g) {
+                    const uint32_t buf = g & 1;
+                    mbar_wait(tmem_empty_bar(buf), ((g >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + buf * Cfg::TILE_N;
+                    const int kb_end = min(num_kb, (ch + 1) * kc);
+                    for (int kb = ch * kc; kb < kb_end; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
+                        const uint64_t da_hi = make_smem_desc<BLOCK_K>(sa);
+                        const uint64_t db_hi = make_smem_desc<BLOCK_K>(sb);
+                        const uint64_t da_lo = make_smem_desc<BLOCK_K>(sa + Cfg::A_BYTES);
+                        const uint64_t db_lo = make_smem_desc<BLOCK_K>(sb + Cfg::B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            const uint32_t first = (kb == ch * kc && k == 0) ? 0u : 1u;
+                            if (TERMS == 3) {
+                                umma_tf32_2sm(tmem_d, da_lo + koff, db_hi + koff, idesc, first);
+                                umma_tf32_2sm(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                                umma_tf32_2sm(tmem_d, da_hi + koff, db_hi + koff, idesc, 1u);
+                            } else {
+                                umma_tf32_2sm(tmem_d, da_hi + koff, db_hi + koff, idesc, first);
+                            }
+                        }
+                        umma_commit_2sm(empty_bar(stage), 0x3);   // frees the stage in BOTH CTAs
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit_2sm(tmem_full_bar(buf), 0x3);     // chunk complete -> both CTAs' epilogues
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================================================= epilogue (warps 2..9, both CTAs, own 128 rows)
+        constexpr int CPW = Cfg::COLS_PER_WARP;
+        const int ew = warp - 2;
+        const int quad = warp & 3;
+        const int col0 = (ew >> 2) * CPW;
+        uint32_t g = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            int m_blk, n_blk;
+            tile_coords(tile, m_blk, n_blk);
+            float acc[CPW];
+            for (int ch = 0; ch < num_chunks; ++ch, ++g) {
+                const uint32_t buf = g & 1;
+                mbar_wait(tmem_full_bar(buf), (g >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < CPW / 32; ++c) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Cfg::TILE_N + col0 + c * 32);
+                    tmem_ld_32x32(taddr, r);
+                    tmem_ld_wait();
+                    if (ch == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c * 32 + j] = __uint_as_float(r[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(r[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_shared(tmem_empty_bar(buf), 0));  // the leader's barrier
+            }
+            const int row = m_blk * Cfg::TILE_M + (int)rank * 128 + quad * 32 + lane;
+            if (row < p.M) {
+                float* crow = p.C + (size_t)row * p.N;
+                const int nbase = n_blk * Cfg::TILE_N + col0;
+#pragma unroll
+                for (int j = 0; j < CPW; j += 4) {
+                    const int n0 = nbase + j;
+                    if (n0 >= p.N) break;
+                    if (p.c_vec_ok && n0 + 4 <= p.N) {
+                        epilogue_store4(p, crow, (size_t)row * p.N, n0, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (n0 + e < p.N) epilogue_store1(p, crow, (size_t)row * p.N, n0 + e, acc[j + e]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still read this CTA's shared memory / signal its barriers
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -545,6 +836,44 @@ static int launch_cfg(sl_ctx* ctx, const GemmParams& p, const float* a_hi, const
     return SL_OK;
 }
 
+// 2-CTA (cta_group::2) launch: clusters of 2 CTAs, one 256x256 tile per cluster; each CTA's TMA box is 128 rows of A / of B
+template <int TERMS, int STAGES>
+static int launch_cfg_2cta(sl_ctx* ctx, const GemmParams& p, const float* a_hi, const float* a_lo, size_t lda, const float* b_hi,
+                           const float* b_lo, size_t ldb) {
+    using Cfg = Gemm2Cfg<TERMS, STAGES>;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_map(ctx, &ma_hi, a_hi, p.M, p.K, lda, Cfg::BLOCK_K, 128)) != SL_OK) return rc;
+    if ((rc = make_map(ctx, &mb_hi, b_hi, p.N, p.K, ldb, Cfg::BLOCK_K, 128)) != SL_OK) return rc;
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+    if (TERMS == 3) {
+        if ((rc = make_map(ctx, &ma_lo, a_lo, p.M, p.K, lda, Cfg::BLOCK_K, 128)) != SL_OK) return rc;
+        if ((rc = make_map(ctx, &mb_lo, b_lo, p.N, p.K, ldb, Cfg::BLOCK_K, 128)) != SL_OK) return rc;
+    }
+    auto kern = gemm_tf32_2cta_kernel<TERMS, STAGES>;
+    SL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    const int num_tiles = ((p.M + Cfg::TILE_M - 1) / Cfg::TILE_M) * ((p.N + Cfg::TILE_N - 1) / Cfg::TILE_N);
+    const int max_clusters = ctx->num_sms / 2;
+    const int grid = 2 * (num_tiles < max_clusters ? num_tiles : max_clusters);
+    sl_ctx::ProfRec rec{};
+    if (ctx->profiling) {
+        cudaEventCreate(&rec.a);
+        cudaEventCreate(&rec.b);
+        rec.flops = 2.0 * p.M * (double)p.N * p.K;
+        cudaEventRecord(rec.a, ctx->stream);
+    }
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    ctx->launches++;
+    if (ctx->profiling) {
+        cudaEventRecord(rec.b, ctx->stream);
+        ctx->prof.push_back(rec);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return sl_set_error(ctx, SL_ERR_CUDA, "gemm_tf32_2cta_kernel launch: %s", cudaGetErrorString(e));
+    return SL_OK;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
@@ -555,18 +884,23 @@ static int env_int(const char* name, int dflt) {
 // Runs the tensor-core kernel on prepared K-major planes: C[M x N] (=|+=) A[M x K] * B[N x K]^T (+ bias, relu).
 // a_lo / b_lo are NULL in TF32 mode.  lda / ldb in floats, multiples of 4, planes 16-byte aligned.
 int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const float* a_lo, size_t lda, const float* b_hi, const float* b_lo,
-                      size_t ldb, float* C, const float* bias, int accumulate, int relu) {
+                      size_t ldb, float* C, const float* bias, int accumulate, int relu, float* c2, const float* mask_src) {
     GemmParams p;
-    p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu;
-    p.c_vec_ok = (N % 4 == 0) && sl_aligned16(C) && (!bias || sl_aligned16(bias));
+    p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu; p.C2 = c2; p.mask_src = mask_src;
+    p.c_vec_ok = (N % 4 == 0) && sl_aligned16(C) && (!bias || sl_aligned16(bias)) && (!c2 || sl_aligned16(c2)) && (!mask_src || sl_aligned16(mask_src));
     const bool three = a_lo != nullptr;
     // K-chunk (in k-blocks of 32) accumulated inside TMEM before promotion to fp32 registers; 0 = whole K (TF32 fast mode)
     p.kc_blocks = three ? env_int("SLICED_GEMM_KC", 4) : env_int("SLICED_GEMM_KC_TF32", 0);
     // tile configuration: SLICED_GEMM_CFG = 0 auto | 1: 128x256x32 | 2: 128x256x16 (swizzle 64B, deeper ring) | 3: 128x128x32
+    //                                       | 4: 2-CTA pairs (cta_group::2), 256x256x32 per pair
     int cfg = env_int("SLICED_GEMM_CFG", 0);
     if (cfg == 0) {
-        const long tiles256 = (long)((M + 127) / 128) * ((N + 255) / 256);
-        cfg = (N <= 128 || tiles256 < ctx->num_sms) ? 3 : 1;
+        const long pair_tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
+        cfg = (M >= 256 && N >= 256 && pair_tiles >= ctx->num_sms / 4) ? 4 : 3;   // enough 256x256 tiles to occupy half the CTA pairs
+    }
+    if (cfg == 4) {  // cta_group::2, 256x256 tile per CTA pair
+        if (three) return launch_cfg_2cta<3, 3>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        return launch_cfg_2cta<1, 6>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
     }
     if (three) {
         if (cfg == 1) return launch_cfg<256, 32, 3, 2>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
@@ -603,8 +937,32 @@ static bool tc_eligible(size_t m, size_t n, size_t k) {
     return m >= min_dim && n >= min_dim && k >= 32 && (double)m * (double)n * (double)k >= (double)(1 << 22);
 }
 
+// fused epilogue request (f32): v = acc (+ C) (+ bias[n]) ; v *= (mask_src >= 0) ; [relu in place] ; C = v ; C2 = relu(v)
+struct Epi {
+    const float* bias = nullptr;
+    int relu = 0;
+    float* c2 = nullptr;
+    const float* mask_src = nullptr;
+    bool any() const { return bias || relu || c2 || mask_src; }
+};
+
+// the same epilogue as a separate pass, for shapes that do not run on the tensor-core kernel (tiny / skinny)
+__global__ void __launch_bounds__(256) epilogue_pass_kernel(size_t total, size_t n, float* C, const float* __restrict__ bias, int relu, float* C2,
+                                                            const float* __restrict__ mask_src) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        float v = C[i];
+        if (bias) v += __ldg(bias + i % n);
+        if (mask_src) v = (__ldg(mask_src + i) >= 0.f ? 1.f : 0.f) * v;
+        if (relu) v = (v >= 0.f ? 1.f : 0.f) * v;
+        C[i] = v;
+        if (C2) C2[i] = (v >= 0.f ? 1.f : 0.f) * v;
+    }
+}
+
 static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
-                        int accumulate, int mode, const float* bias, int relu) {
+                        int accumulate, int mode, const Epi& epi) {
+    const float* bias = epi.bias;
+    const int relu = epi.relu;
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     if (m == 0 || n == 0) return SL_OK;
     SL_REQUIRE(ctx, c != nullptr, "NULL output");
@@ -612,12 +970,17 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
     SL_REQUIRE(ctx, a && b, "NULL operand");
     if (mode < 0) mode = ctx->gemm_mode;
     if (dtype != SL_F32 || mode == SL_GEMM_SIMT || !tc_eligible(m, n, k)) {
-        if (bias || relu) return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "fused epilogue needs the tensor-core path");
-        if (dtype == SL_F32 && mode != SL_GEMM_SIMT) {  // HBM-bound skinny shapes (n <= 16 or k <= 16) have their own kernels
-            int rc = sl_gemm_skinny_f32(ctx, trans_a, trans_b, m, n, k, (const float*)a, (const float*)b, (float*)c, accumulate);
-            if (rc <= 0) return rc;
-        }
-        return sl_gemm_simt(ctx, dtype, trans_a, trans_b, m, n, k, a, b, c, accumulate);
+        if (epi.any() && dtype != SL_F32) return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "fused epilogue is f32 only");
+        int rc = 1;
+        if (dtype == SL_F32 && mode != SL_GEMM_SIMT)  // HBM-bound skinny shapes (n <= 16 or k <= 16) have their own kernels
+            rc = sl_gemm_skinny_f32(ctx, trans_a, trans_b, m, n, k, (const float*)a, (const float*)b, (float*)c, accumulate);
+        if (rc > 0) rc = sl_gemm_simt(ctx, dtype, trans_a, trans_b, m, n, k, a, b, c, accumulate);
+        if (rc != SL_OK || !epi.any()) return rc;
+        const size_t total = m * n;
+        const size_t cap = (size_t)ctx->num_sms * 8;
+        size_t blocks = (total + 255) / 256;
+        SL_LAUNCH(ctx, epilogue_pass_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, total, n, (float*)c, bias, relu, epi.c2, epi.mask_src);
+        return SL_OK;
     }
     const bool three = mode == SL_GEMM_3XTF32;
     const size_t ldp = (k + 3) & ~size_t(3);
@@ -651,26 +1014,48 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
         if (rc != SL_OK) return rc;
         b_hi = h; b_lo = l; ldb = ldp;
     }
-    return sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, lda, b_hi, b_lo, ldb, (float*)c, bias, accumulate, relu);
+    return sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, lda, b_hi, b_lo, ldb, (float*)c, bias, accumulate, relu, epi.c2, epi.mask_src);
 }
 
 extern "C" {
 
 int sl_gemm_ex(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
                int accumulate, int mode) {
-    return gemm_ex_impl(ctx, dtype, trans_a, trans_b, m, n, k, a, b, c, accumulate, mode, nullptr, 0);
+    return gemm_ex_impl(ctx, dtype, trans_a, trans_b, m, n, k, a, b, c, accumulate, mode, Epi{});
 }
 
 int sl_gemm(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, void* out, int mode) {
-    return gemm_ex_impl(ctx, dtype, 0, 0, m, n, k, lhs, rhs, out, 0, mode, nullptr, 0);
+    return gemm_ex_impl(ctx, dtype, 0, 0, m, n, k, lhs, rhs, out, 0, mode, Epi{});
 }
 
 int sl_gemm_nt(sl_ctx* ctx, int dtype, size_t m, size_t n, size_t k, const void* a, const void* b, void* c, int mode) {
-    return gemm_ex_impl(ctx, dtype, 0, 1, m, n, k, a, b, c, 0, mode, nullptr, 0);
+    return gemm_ex_impl(ctx, dtype, 0, 1, m, n, k, a, b, c, 0, mode, Epi{});
 }
 
 int sl_gemm_tn(sl_ctx* ctx, int dtype, size_t m, size_t n, size_t k, const void* a, const void* b, void* c, int mode) {
-    return gemm_ex_impl(ctx, dtype, 1, 0, m, n, k, a, b, c, 0, mode, nullptr, 0);
+    return gemm_ex_impl(ctx, dtype, 1, 0, m, n, k, a, b, c, 0, mode, Epi{});
+}
+
+int sl_linear_fwd(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, const void* bias, void* z_out,
+                  void* act_out, int mode) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    SL_REQUIRE(ctx, dtype == SL_F32, "sl_linear_fwd is f32 only");
+    SL_REQUIRE(ctx, z_out != nullptr, "z_out is NULL");
+    Epi e;
+    e.bias = (const float*)bias;
+    e.c2 = (float*)act_out;
+    return gemm_ex_impl(ctx, dtype, 0, 0, m, n, k, lhs, rhs, z_out, 0, mode, e);
+}
+
+int sl_linear_bwd_input_relu(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* rhs, const void* out_grad, const void* z_prev,
+                             void* x_grad, int mode) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    SL_REQUIRE(ctx, dtype == SL_F32, "sl_linear_bwd_input_relu is f32 only");
+    SL_REQUIRE(ctx, x_grad != nullptr, "x_grad is NULL");
+    Epi e;
+    e.mask_src = (const float*)z_prev;
+    // gemmT(m, k, n, out_grad, rhs, x_grad) (gemm/grad/cpu_stack.rs:36) with the relu gradient (src/matrix.rs:186) in the epilogue
+    return gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, x_grad, 0, mode, e);
 }
 
 int sl_gemm_grad(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, void* lhs_grad, void* rhs_grad,
@@ -678,11 +1063,11 @@ int sl_gemm_grad(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const voi
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     SL_REQUIRE(ctx, out_grad != nullptr || m == 0 || n == 0, "NULL out_grad");
     if (lhs_grad) {  // gemmT(m, k, n, out_grad, rhs, lhs_grad): lhs_grad[m x k] = out_grad[m x n] * rhs[k x n]^T
-        int rc = gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, lhs_grad, accumulate, mode, nullptr, 0);
+        int rc = gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, lhs_grad, accumulate, mode, Epi{});
         if (rc != SL_OK) return rc;
     }
     if (rhs_grad) {  // Tgemm(k, n, m, lhs, out_grad, rhs_grad): rhs_grad[k x n] = lhs[m x k]^T * out_grad[m x n]
-        int rc = gemm_ex_impl(ctx, dtype, 1, 0, k, n, m, lhs, out_grad, rhs_grad, accumulate, mode, nullptr, 0);
+        int rc = gemm_ex_impl(ctx, dtype, 1, 0, k, n, m, lhs, out_grad, rhs_grad, accumulate, mode, Epi{});
         if (rc != SL_OK) return rc;
     }
     return SL_OK;

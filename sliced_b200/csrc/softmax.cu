@@ -135,12 +135,13 @@ __global__ void __launch_bounds__(1024) softmax_block_kernel(size_t samples, siz
             }
         }
         sum = block_reduce<T, false>(sum, s_buf);
+        const T inv = T(1) / sum;  // one IEEE division per row; e * (1/s) is within 1 ulp of e / s (tolerance: K-scaled)
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             const size_t i = (size_t)k * blockDim.x + threadIdx.x;
             if (i < packs) {
 #pragma unroll
-                for (int e = 0; e < V; ++e) p[k].v[e] = p[k].v[e] / sum;
+                for (int e = 0; e < V; ++e) p[k].v[e] = p[k].v[e] * inv;
                 st_stream(out + r * features + i * V, p[k]);
             }
         }

@@ -67,6 +67,7 @@ def _lib():
             "slh_mlp_grad_bucket": ([_vp], _vp),
             "slh_mlp_params": ([_vp], _vp),
             "slh_mlp_forward_backward": ([_vp, _vp, _vp, _vp, _sz, _sz, _i, P(_d), P(C.c_longlong)], _i),
+            "slh_mlp_set_fused": ([_vp, _i], None),
             "slh_mlp_allreduce_grads": ([_vp], _i),
             "slh_mlp_sgd": ([_vp, _d], _i),
             "slh_mlp_step": ([_vp, _vp, _vp, _vp, _sz, _sz, _d, _i, P(_d), P(C.c_longlong)], _i),
@@ -321,6 +322,7 @@ class Mlp:
                                              C.byref(loss), C.byref(correct)))
         return loss.value, correct.value
 
+    def set_fused(self, on: bool): _lib().slh_mlp_set_fused(self.h, int(on))
     def allreduce_grads(self): _chk(_lib().slh_mlp_allreduce_grads(self.h))
     def sgd(self, lr): _chk(_lib().slh_mlp_sgd(self.h, lr))
 

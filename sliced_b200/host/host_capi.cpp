@@ -171,6 +171,7 @@ int slh_mlp_forward_backward(slh_mlp* m, slh_buffer* x, slh_buffer* y, slh_buffe
         return 0;
     }, -1);
 }
+void slh_mlp_set_fused(slh_mlp* m, int on) { ((Mlp*)m)->set_fused(on != 0); }
 int slh_mlp_allreduce_grads(slh_mlp* m) { return guard([&]() { ((Mlp*)m)->allreduce_grads(); return 0; }, -1); }
 int slh_mlp_sgd(slh_mlp* m, double lr) { return guard([&]() { ((Mlp*)m)->sgd(lr); return 0; }, -1); }
 int slh_mlp_step(slh_mlp* m, slh_buffer* x, slh_buffer* y, slh_buffer* labels, size_t batch, size_t grad_rows, double lr, int want_metrics,

@@ -86,6 +86,73 @@ StepResult Mlp::forward_backward(const Buf& x, const Buf& y, const Buf& labels, 
     return r;
 }
 
+StepResult Mlp::read_metrics(bool want) {
+    StepResult r;
+    if (want) {
+        struct { float loss; int32_t correct; } m;
+        dev_.check(sl_read(dev_.ctx(), &m, metrics_dev_, 8));
+        r.loss_sum = m.loss;
+        r.correct = m.correct;
+    }
+    return r;
+}
+
+StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics) {
+    Device& d = dev_;
+    sl_ctx* c = d.ctx();
+    const size_t L = layers_.size();
+    const size_t oc = dims_.back();
+    if (fused_batch_ != batch) {  // (re)allocate the persistent activations: z_l, a_l = relu(z_l), gz_l = d loss / d z_l
+        z_.clear(); a_.clear(); gz_.clear();
+        for (size_t l = 0; l < L; ++l) {
+            z_.push_back(d.buffer(batch * dims_[l + 1], SL_F32));
+            a_.push_back(d.buffer(batch * dims_[l + 1], SL_F32));
+            gz_.push_back(d.buffer(batch * dims_[l + 1], SL_F32));
+        }
+        loss_tmp_[0] = d.buffer(batch * oc, SL_F32);  // clip(out) * y
+        loss_tmp_[1] = d.buffer(batch, SL_F32);       // per-sample loss
+        loss_tmp_[2] = d.buffer(batch * oc, SL_F32);  // cce_grad
+        fused_batch_ = batch;
+    }
+    // parameter gradients accumulate (bias: += column sums) -> zero the bucket; activation gradients are all SET
+    d.check(sl_clear(c, bucket_->dptr, bucket_->bytes()));
+    d.check(sl_clear(c, metrics_dev_, 16));
+
+    // ---- forward: Linear + relu fused; the 10-class head goes through the skinny kernel + add_row_mut + softmax
+    const void* in = x->dptr;
+    for (size_t l = 0; l < L; ++l) {
+        const bool last = l + 1 == L;
+        d.check(sl_linear_fwd(c, SL_F32, batch, dims_[l], dims_[l + 1], in, layers_[l].weights.data->dptr, layers_[l].bias.data->dptr,
+                              z_[l]->dptr, last ? nullptr : a_[l]->dptr, -1));
+        in = a_[l]->dptr;
+    }
+    Buf out = a_[L - 1];
+    d.check(sl_softmax(c, SL_F32, batch, oc, z_[L - 1]->dptr, out->dptr));
+    if (labels) d.check(sl_count_correct(c, SL_F32, batch, oc, out->dptr, (const int32_t*)labels->dptr, (int32_t*)metrics_dev_ + 1));
+    // cce / cce_grad exactly as nn.rs:124-152 (tiny: batch x 10)
+    const size_t on = batch * oc;
+    d.check(sl_unary(c, SL_F32, SL_UN_CLIP, 1E-7, 1. - 1E-7, out->dptr, loss_tmp_[0]->dptr, on));
+    d.check(sl_binary_ew(c, SL_F32, SL_MUL, loss_tmp_[0]->dptr, y->dptr, loss_tmp_[0]->dptr, on));
+    d.check(sl_sum_cols(c, SL_F32, batch, oc, loss_tmp_[0]->dptr, loss_tmp_[1]->dptr));
+    d.check(sl_unary(c, SL_F32, SL_UN_NEG_LN, 0, 0, loss_tmp_[1]->dptr, loss_tmp_[1]->dptr, batch));
+    d.check(sl_sum(c, SL_F32, loss_tmp_[1]->dptr, batch, metrics_dev_));
+    d.check(sl_binary_ew(c, SL_F32, SL_DIV, y->dptr, out->dptr, loss_tmp_[2]->dptr, on));
+    d.check(sl_unary(c, SL_F32, SL_UN_NEG_DIV_SCALAR, (double)grad_rows, 0, loss_tmp_[2]->dptr, loss_tmp_[2]->dptr, on));
+
+    // ---- backward: the tape of nn.rs in reverse, with gemm_grad(lhs) + relu grad fused
+    d.check(sl_softmax_grad(c, SL_F32, batch, oc, gz_[L - 1]->dptr, out->dptr, loss_tmp_[2]->dptr));       // SET
+    for (size_t li = L; li-- > 0;) {
+        const size_t I = dims_[li], O = dims_[li + 1];
+        const void* lin = li == 0 ? x->dptr : a_[li - 1]->dptr;
+        d.check(sl_add_row_mut_grad(c, SL_F32, batch, O, d.grad(layers_[li].bias.data)->dptr, gz_[li]->dptr));   // b.grad += colsum
+        d.check(sl_gemm_tn(c, SL_F32, I, O, batch, lin, gz_[li]->dptr, d.grad(layers_[li].weights.data)->dptr, -1));  // Tgemm(k,n,m,lhs,og,W.grad) SET
+        if (li > 0)
+            d.check(sl_linear_bwd_input_relu(c, SL_F32, batch, I, O, layers_[li].weights.data->dptr, gz_[li]->dptr, z_[li - 1]->dptr,
+                                             gz_[li - 1]->dptr, -1));
+    }
+    return read_metrics(want_metrics);
+}
+
 void Mlp::allreduce_grads() { dev_.check(sl_allreduce_sum(dev_.ctx(), SL_F32, bucket_->dptr, n_params_)); }
 
 void Mlp::sgd(double lr) {

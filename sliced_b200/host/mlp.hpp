@@ -52,10 +52,20 @@ class Mlp {
     // labels: int32 [batch] or null.  grad_rows: the `rows` of cce_grad (nn.rs:151) — the global batch under DP.
     // Phases can be run separately so that a data-parallel driver can put the exchange between backward and sgd.
     StepResult forward_backward(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics);
+    // The same step with the chains the tape exposes fused (what custos' `Lazy` graph + `optimize()` hook is for, nn.rs:302):
+    //   gemm -> add_row_mut -> relu            => one gemm with a bias + relu epilogue (sl_linear_fwd)
+    //   gemm_grad(lhs) -> relu grad            => one gemm with a relu-mask epilogue (sl_linear_bwd_input_relu)
+    //   zero_grad of activation gradients      => dropped: every activation gradient is produced by a SET kernel
+    // Every per-element operation and its order are those of the unfused step, so losses, gradients and weights are
+    // bit-identical to forward_backward() (tests/test_gpu_mlp.py::test_fused_step_is_bit_identical).
+    StepResult forward_backward_fused(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics);
+    void set_fused(bool on) { fused_ = on; }
+    bool fused() const { return fused_; }
     void allreduce_grads();          // sl_allreduce_sum over the bucket (no-op for a world of one)
     void sgd(double lr);             // SGD::step on every Linear (nn.rs:235-237)
     StepResult step(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, double lr, bool want_metrics) {
-        StepResult r = forward_backward(x, y, labels, batch, grad_rows, want_metrics);
+        StepResult r = (fused_ && loss_ == LOSS_SOFTMAX_CCE) ? forward_backward_fused(x, y, labels, batch, grad_rows, want_metrics)
+                                                                : forward_backward(x, y, labels, batch, grad_rows, want_metrics);
         allreduce_grads();
         sgd(lr);
         return r;
@@ -71,6 +81,12 @@ class Mlp {
     Buf bucket_;
     size_t n_params_ = 0;
     void* metrics_dev_ = nullptr;  // [loss_sum f32][correct i32]
+    bool fused_ = false;
+    // persistent activations / activation gradients of the fused step (sized for the last batch seen)
+    size_t fused_batch_ = 0;
+    std::vector<Buf> z_, a_, gz_;
+    Buf loss_tmp_[4];
+    StepResult read_metrics(bool want);
 };
 
 }  // namespace slh

@@ -95,7 +95,7 @@ def test_tensor_core_gemm(ctx, shape, trans, mode):
         assert err <= 8 * np.sqrt(k) * 2.0 ** -11, f"TF32 err {err}"
 
 
-@pytest.mark.parametrize("cfg", ["1", "2", "3"])
+@pytest.mark.parametrize("cfg", ["1", "2", "3", "4"])
 @pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
 def test_tile_configs(cfg, mode):
     """every tile configuration of the tcgen05 kernel (SLICED_GEMM_CFG) gives the same answers; tails included"""

@@ -103,3 +103,56 @@ def test_dp_grad_scaling_equals_single_device():
     a = grads(x[:h * 64], y[:h * 10], labels[:h], batch)
     b = grads(x[h * 64:], y[h * 10:], labels[h:], batch)
     assert np.max(np.abs((a + b) - full)) <= 1e-5 * np.max(np.abs(full))
+
+
+@pytest.mark.parametrize("dims,batch", [([12, 16, 8, 10], 32), ([256, 512, 384, 10], 1024), ([512, 768, 512, 10], 2048)])
+def test_fused_step_is_bit_identical(dims, batch):
+    """Mlp.set_fused(True): gemm+add_row_mut+relu and gemm_grad+relu-grad run as single kernels with fused epilogues and the
+    activation-gradient memsets disappear — losses, accuracy, gradients and weights must equal the op-by-op tape EXACTLY."""
+    from sliced_b200.host import CUDA, Mlp
+    x, y, labels, W, B = make_problem(dims, batch, 5)
+    res = []
+    for fused in (False, True):
+        dev = CUDA(0, cached=True)
+        mlp = Mlp(dev, dims, 0)
+        mlp.set_fused(fused)
+        for l in range(len(dims) - 1):
+            mlp.weights(l).write(W[l]); mlp.bias(l).write(B[l])
+        dx, dy, dl = dev.buffer(x).no_grad(), dev.buffer(y).no_grad(), dev.buffer(labels)
+        hist = [mlp.step(dx, dy, dl, batch, 0.1) for _ in range(3)]
+        res.append((hist, mlp.params().read(), mlp.grad_bucket().read(), dev.launches))
+        del mlp, dx, dy, dl
+        dev.close()
+    (h0, p0, g0, n0), (h1, p1, g1, n1) = res
+    assert h0 == h1
+    assert np.array_equal(g0, g1), np.max(np.abs(g0 - g1))
+    assert np.array_equal(p0, p1)
+    assert n1 < n0, (n0, n1)
+
+
+def test_fused_entry_points_equal_composition():
+    """sl_linear_fwd == sl_gemm + sl_add_row_mut + relu ; sl_linear_bwd_input_relu == gemm_grad(lhs) + relu grad into zeros"""
+    import ctypes as C
+    import sliced_b200 as S
+    ctx = S.Context(0)
+    L = ctx.lib
+    rng = np.random.default_rng(1)
+    for (m, k, n) in [(512, 384, 640), (100, 64, 10), (1000, 4096, 10), (300, 10, 512)]:
+        lhs, rhs = ctx.array(rng.uniform(-1, 1, m * k).astype(np.float32)), ctx.array(rng.uniform(-1, 1, k * n).astype(np.float32))
+        bias = ctx.array(rng.uniform(-1, 1, n).astype(np.float32))
+        z_ref = ctx.gemm(m, k, n, lhs, rhs)
+        ctx.add_row_mut(m, n, z_ref, bias)
+        a_ref = ctx.unary(S.UN_RELU, z_ref)
+        z, a = ctx.zeros(m * n), ctx.zeros(m * n)
+        S.capi.check(ctx.h, L.sl_linear_fwd(ctx.h, S.F32, m, k, n, lhs.ptr, rhs.ptr, bias.ptr, z.ptr, a.ptr, -1))
+        assert np.array_equal(z.numpy(), z_ref.numpy()) and np.array_equal(a.numpy(), a_ref.numpy())
+        og = ctx.array(rng.uniform(-1, 1, m * n).astype(np.float32))
+        zprev = ctx.array(rng.uniform(-1, 1, m * k).astype(np.float32))
+        ga = ctx.zeros(m * k)
+        ctx.gemm_grad(m, k, n, lhs, rhs, ga, None, og)
+        gz_ref = ctx.zeros(m * k)
+        ctx.unary_grad(S.UN_RELU, zprev, gz_ref, ga)
+        gz = ctx.array(rng.uniform(-1, 1, m * k).astype(np.float32))  # junk: the fused kernel is SET
+        S.capi.check(ctx.h, L.sl_linear_bwd_input_relu(ctx.h, S.F32, m, k, n, rhs.ptr, og.ptr, zprev.ptr, gz.ptr, -1))
+        assert np.array_equal(gz.numpy(), gz_ref.numpy())
+    ctx.close()
