@@ -306,6 +306,11 @@ int sl_comm_unique_id(void* id_out_128);
 int sl_comm_init_rank(sl_ctx* ctx, int nranks, int rank, const void* id_128);
 /* In-place sum all-reduce of a device buffer across the ranks of the communicator (NCCL over NVLink). */
 int sl_allreduce_sum(sl_ctx* ctx, int dtype, void* buf, size_t n);
+/* Overlapped variant: the all-reduce is enqueued on the context's communication stream, ordered after everything issued so far on
+ * the compute stream, and the compute stream continues (e.g. with the remaining backward gemms).  sl_comm_wait makes the compute
+ * stream wait for every exchange issued so far (call it before the SGD step reads the gradients). */
+int sl_allreduce_sum_async(sl_ctx* ctx, int dtype, void* buf, size_t n);
+int sl_comm_wait(sl_ctx* ctx);
 int sl_comm_destroy(sl_ctx* ctx);
 
 #ifdef __cplusplus

@@ -136,6 +136,8 @@ def _declare(lib):
         "sl_comm_unique_id": ([_vp], _i),
         "sl_comm_init_rank": ([_vp, _i, _i, _vp], _i),
         "sl_allreduce_sum": ([_vp, _i, _vp, _sz], _i),
+        "sl_allreduce_sum_async": ([_vp, _i, _vp, _sz], _i),
+        "sl_comm_wait": ([_vp], _i),
         "sl_comm_destroy": ([_vp], _i),
     }
     for name, (args, res) in sig.items():

@@ -95,7 +95,47 @@ int sl_allreduce_sum(sl_ctx* ctx, int dtype, void* buf, size_t n) {
     return SL_OK;
 }
 
+// Overlapped exchange: the all-reduce runs on the context's communication stream, ordered after everything issued so far on
+// the compute stream (so the gradient segment is complete), while the compute stream carries on with the rest of backward.
+int sl_allreduce_sum_async(sl_ctx* ctx, int dtype, void* buf, size_t n) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (n == 0) return SL_OK;
+    SL_REQUIRE(ctx, buf != nullptr, "NULL buffer");
+    if (!ctx->nccl_comm) {
+        if (ctx->nranks <= 1) return SL_OK;
+        return sl_set_error(ctx, SL_ERR_NCCL, "sl_allreduce_sum_async: communicator not initialised");
+    }
+    if (!ctx->comm_stream) {
+        SL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+        SL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->comm_ready, cudaEventDisableTiming));
+        SL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
+    }
+    SL_CUDA(ctx, cudaEventRecord(ctx->comm_ready, ctx->stream));
+    SL_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ready, 0));
+    const int dt = dtype == SL_F32 ? ncclFloat32 : (dtype == SL_F64 ? ncclFloat64 : ncclInt32);
+    SL_NCCL(ctx, nccl().AllReduce(buf, buf, n, dt, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->comm_stream));
+    ctx->comm_pending = true;
+    return SL_OK;
+}
+
+// The compute stream waits for every exchange issued with sl_allreduce_sum_async.
+int sl_comm_wait(sl_ctx* ctx) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (!ctx->comm_stream || !ctx->comm_pending) return SL_OK;
+    SL_CUDA(ctx, cudaEventRecord(ctx->comm_done, ctx->comm_stream));
+    SL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->comm_done, 0));
+    ctx->comm_pending = false;
+    return SL_OK;
+}
+
 int sl_comm_destroy(sl_ctx* ctx) {
+    if (ctx && ctx->comm_stream) {
+        cudaStreamSynchronize(ctx->comm_stream);
+        cudaStreamDestroy(ctx->comm_stream);
+        cudaEventDestroy(ctx->comm_ready);
+        cudaEventDestroy(ctx->comm_done);
+        ctx->comm_stream = nullptr;
+    }
     if (!ctx || !ctx->nccl_comm) return SL_OK;
     if (nccl().ok) nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;

@@ -35,6 +35,9 @@ struct sl_ctx {
     void* nccl_comm = nullptr;
     int nranks = 1;
     int rank = 0;
+    cudaStream_t comm_stream = nullptr;  // overlapped exchange (sl_allreduce_sum_async)
+    cudaEvent_t comm_ready = nullptr, comm_done = nullptr;
+    bool comm_pending = false;
 };
 
 int sl_set_error(sl_ctx* ctx, int code, const char* fmt, ...);

@@ -170,6 +170,7 @@ struct GemmParams {
     int relu;           // C = (v >= 0) * v after bias
     int c_vec_ok;       // N % 4 == 0 and C 16-byte aligned
     int kc_blocks;      // k-blocks per TMEM accumulation chunk
+    int splits;             // split-K factor (2-CTA kernel): partial s is written to C + s*M*N, folded afterwards by the host
     float* C2;              // optional second output: C2 = (v >= 0) * v of the value stored to C (fused Matrix::relu)
     const float* mask_src;  // optional [M x N]: v *= (mask_src >= 0) before the store (fused relu gradient)
 };
@@ -539,7 +540,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     const int num_tiles = num_m * num_n;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
     const int kc = p.kc_blocks > 0 ? p.kc_blocks : num_kb;
-    const int num_chunks = (num_kb + kc - 1) / kc;
+    // split-K: a work unit is (tile, split); split s covers k-blocks [s*kbs, (s+1)*kbs) and writes its partial tile to
+    // C + s*M*N (the host points C at scratch and folds the partials in order afterwards)
+    const int splits = p.splits > 0 ? p.splits : 1;
+    const int kbs = (num_kb + splits - 1) / splits;
+    const int num_units = num_tiles * splits;
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
     auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
@@ -557,12 +562,13 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
                 int m_blk, n_blk;
-                tile_coords(tile, m_blk, n_blk);
+                tile_coords(unit / splits, m_blk, n_blk);
+                const int kb0 = (unit % splits) * kbs, kb1 = min(num_kb, kb0 + kbs);
                 const int row_a = m_blk * Cfg::TILE_M + (int)rank * 128;
                 const int row_b = n_blk * Cfg::TILE_N + (int)rank * 128;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
@@ -589,14 +595,17 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             int stage = 0;
             uint32_t phase = 0;
             uint32_t g = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+                const int kb0 = (unit % splits) * kbs, kb1 = min(num_kb, kb0 + kbs);
+                const int num_chunks = (kb1 - kb0 + kc - 1) / kc;
                 for (int ch = 0; ch < num_chunks; ++ch, ++g) {
                     const uint32_t buf = g & 1;
                     mbar_wait(tmem_empty_bar(buf), ((g >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + buf * Cfg::TILE_N;
-                    const int kb_end = min(num_kb, (ch + 1) * kc);
-                    for (int kb = ch * kc; kb < kb_end; ++kb) {
+                    const int kb_begin = kb0 + ch * kc;
+                    const int kb_end = min(kb1, kb_begin + kc);
+                    for (int kb = kb_begin; kb < kb_end; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -608,7 +617,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            const uint32_t first = (kb == ch * kc && k == 0) ? 0u : 1u;
+                            const uint32_t first = (kb == kb_begin && k == 0) ? 0u : 1u;
                             if (TERMS == 3) {
                                 umma_tf32_2sm(tmem_d, da_lo + koff, db_hi + koff, idesc, first);
                                 umma_tf32_2sm(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
@@ -635,9 +644,12 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         const int quad = warp & 3;
         const int col0 = (ew >> 2) * CPW;
         uint32_t g = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
             int m_blk, n_blk;
-            tile_coords(tile, m_blk, n_blk);
+            tile_coords(unit / splits, m_blk, n_blk);
+            const int split = unit % splits;
+            const int kb0 = split * kbs, kb1 = min(num_kb, kb0 + kbs);
+            const int num_chunks = (kb1 - kb0 + kc - 1) / kc;
             float acc[CPW];
             for (int ch = 0; ch < num_chunks; ++ch, ++g) {
                 const uint32_t buf = g & 1;
@@ -663,7 +675,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             }
             const int row = m_blk * Cfg::TILE_M + (int)rank * 128 + quad * 32 + lane;
             if (row < p.M) {
-                float* crow = p.C + (size_t)row * p.N;
+                float* crow = p.C + (size_t)split * p.M * p.N + (size_t)row * p.N;
                 const int nbase = n_blk * Cfg::TILE_N + col0;
 #pragma unroll
                 for (int j = 0; j < CPW; j += 4) {
@@ -881,6 +893,21 @@ static int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+// folds split-K partials in split order and applies the epilogue (see sl_gemm_tc_planes)
+__global__ void __launch_bounds__(256) splitk_fold_kernel(size_t total, size_t n, int splits, const float* __restrict__ partial, float* C, int accumulate,
+                                                          const float* __restrict__ bias, int relu, float* C2, const float* __restrict__ mask_src) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        float v = partial[i];
+        for (int s = 1; s < splits; ++s) v += partial[(size_t)s * total + i];
+        if (accumulate) v += C[i];
+        if (bias) v += __ldg(bias + i % n);
+        if (mask_src) v = (__ldg(mask_src + i) >= 0.f ? 1.f : 0.f) * v;
+        if (relu) v = (v >= 0.f ? 1.f : 0.f) * v;
+        C[i] = v;
+        if (C2) C2[i] = (v >= 0.f ? 1.f : 0.f) * v;
+    }
+}
+
 // Runs the tensor-core kernel on prepared K-major planes: C[M x N] (=|+=) A[M x K] * B[N x K]^T (+ bias, relu).
 // a_lo / b_lo are NULL in TF32 mode.  lda / ldb in floats, multiples of 4, planes 16-byte aligned.
 int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const float* a_lo, size_t lda, const float* b_hi, const float* b_lo,
@@ -898,9 +925,42 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const
         const long pair_tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
         cfg = (M >= 256 && N >= 256 && pair_tiles >= ctx->num_sms / 4) ? 4 : 3;   // enough 256x256 tiles to occupy half the CTA pairs
     }
+    p.splits = 1;
     if (cfg == 4) {  // cta_group::2, 256x256 tile per CTA pair
-        if (three) return launch_cfg_2cta<3, 3>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
-        return launch_cfg_2cta<1, 6>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        // Wave quantisation: with T tiles on 74 CTA pairs the last wave is T mod 74 wide (dW of the MLP: 256 tiles = 3.46 waves
+        // -> 4).  When that wastes > 8 % and K is long, split K so that tiles x splits fills whole waves; the partial tiles go
+        // to scratch and are folded in split order (deterministic), the fold also applies the epilogue.
+        const long tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
+        const long pairs = ctx->num_sms / 2;
+        auto eff = [&](long units) { return (double)units / (double)(((units + pairs - 1) / pairs) * pairs); };
+        int best = 1;
+        const int num_kb = (K + 31) / 32;
+        const int max_splits = env_int("SLICED_GEMM_MAX_SPLITS", 4);
+        if (eff(tiles) < 0.92)
+            for (int sp = 2; sp <= max_splits; ++sp) {
+                const int kbs = (num_kb + sp - 1) / sp;
+                if (kbs < 64 || (long)(sp - 1) * kbs >= num_kb) continue;   // keep every split >= 2048 deep and non-empty
+                if (eff(tiles * sp) > eff(tiles * best) + 0.03) best = sp;
+            }
+        GemmParams q = p;
+        float* final_c = C;
+        if (best > 1) {
+            void* ws = nullptr;
+            int rc = sl_ws_reserve(ctx, (size_t)best * M * N * sizeof(float), &ws);
+            if (rc != SL_OK) return rc;
+            q.splits = best;
+            q.C = (float*)ws;
+            q.bias = nullptr; q.accumulate = 0; q.relu = 0; q.C2 = nullptr; q.mask_src = nullptr;
+            q.c_vec_ok = (N % 4 == 0);
+        }
+        int rc = three ? launch_cfg_2cta<3, 3>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb) : launch_cfg_2cta<1, 6>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        if (rc != SL_OK || best == 1) return rc;
+        const size_t total = (size_t)M * N;
+        const size_t cap = (size_t)ctx->num_sms * 8;
+        size_t blocks = (total + 255) / 256;
+        SL_LAUNCH(ctx, splitk_fold_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, total, (size_t)N, best, (const float*)q.C, final_c, p.accumulate,
+                  p.bias, p.relu, p.C2, p.mask_src);
+        return SL_OK;
     }
     if (three) {
         if (cfg == 1) return launch_cfg<256, 32, 3, 2>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);

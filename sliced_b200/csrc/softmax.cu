@@ -148,6 +148,110 @@ __global__ void __launch_bounds__(1024) softmax_block_kernel(size_t samples, siz
     }
 }
 
+// ---------------------------------------------------------------- forward, long rows: bulk-async (TMA engine) row pipeline
+// One persistent 512-thread CTA per SM; rows travel HBM -> shared memory -> HBM with cp.async.bulk (1-D TMA) through a ring of
+// 3 row buffers, so the load of row i+2 and the store of row i-1 are in flight while row i is being reduced in registers.
+// The register-only variant above stops issuing memory traffic during its two block-wide reductions and its expf phase
+// (measured 54-69 % of HBM peak at 16384 features); here HBM never idles.
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load_row(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store_row(void* gdst, uint32_t smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+
+template <typename T, int NP>
+__global__ void __launch_bounds__(512, 1) softmax_pipe_kernel(size_t samples, size_t features, const T* __restrict__ x, T* __restrict__ out) {
+    constexpr int V = Pack<T>::N;
+    constexpr int NBUF = 3;
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    __shared__ T s_buf[32];
+    __shared__ __align__(8) unsigned long long bars[NBUF];
+    const uint32_t row_bytes = (uint32_t)(features * sizeof(T));
+    const size_t packs = features / V;
+    const size_t nrows = samples > blockIdx.x ? (samples - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;  // rows of this CTA
+    auto row_of = [&](size_t i) { return (size_t)blockIdx.x + i * gridDim.x; };
+    auto buf_ptr = [&](int b) { return reinterpret_cast<T*>(sm_raw + (size_t)b * row_bytes); };
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NBUF; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_u32(&bars[b])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (size_t i = 0; i < 2 && i < nrows; ++i)
+            bulk_load_row(sm_u32(buf_ptr((int)i)), x + row_of(i) * features, row_bytes, sm_u32(&bars[i]));
+    }
+    __syncthreads();
+    for (size_t i = 0; i < nrows; ++i) {
+        const int b = (int)(i % NBUF);
+        bar_wait_parity(sm_u32(&bars[b]), (uint32_t)((i / NBUF) & 1));
+        T* row = buf_ptr(b);
+        Pack<T> p[NP];
+        T mx = row[0];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const size_t j = (size_t)k * blockDim.x + threadIdx.x;
+            if (j < packs) {
+                p[k] = *reinterpret_cast<const Pack<T>*>(row + j * V);
+#pragma unroll
+                for (int e = 0; e < V; ++e) mx = p[k].v[e] > mx ? p[k].v[e] : mx;
+            }
+        }
+        mx = block_reduce<T, true>(mx, s_buf);
+        T sum = T(0);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const size_t j = (size_t)k * blockDim.x + threadIdx.x;
+            if (j < packs) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    p[k].v[e] = m_exp(p[k].v[e] - mx);
+                    sum += p[k].v[e];
+                }
+            }
+        }
+        sum = block_reduce<T, false>(sum, s_buf);
+        const T inv = T(1) / sum;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            const size_t j = (size_t)k * blockDim.x + threadIdx.x;
+            if (j < packs) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) p[k].v[e] = p[k].v[e] * inv;
+                *reinterpret_cast<Pack<T>*>(row + j * V) = p[k];
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_store_row(out + row_of(i) * features, sm_u32(row), row_bytes);
+            if (i + 2 < nrows) {
+                // buffer (i+2)%3 was last stored from at iteration i-1: at most the store just committed may still be reading
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                const int nb = (int)((i + 2) % NBUF);
+                bulk_load_row(sm_u32(buf_ptr(nb)), x + row_of(i + 2) * features, row_bytes, sm_u32(&bars[nb]));
+            }
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA's smem is released
+    __syncthreads();
+}
+
 // generic fallback: block per row, re-reads the row (any length / alignment)
 template <typename T>
 __global__ void __launch_bounds__(256) softmax_loop_kernel(size_t samples, size_t features, const T* __restrict__ x, T* __restrict__ out) {
@@ -288,6 +392,22 @@ int softmax_t(sl_ctx* ctx, size_t samples, size_t features, const void* x, void*
         return SL_OK;
     }
     const bool vec = (features % Pack<T>::N == 0) && sl_aligned16(x) && sl_aligned16(out);
+    const size_t row_bytes = features * sizeof(T);
+    if (vec && row_bytes > 8192 && row_bytes <= 65536 && samples >= (size_t)ctx->num_sms && !getenv("SLICED_SOFTMAX_NO_PIPE")) {
+        const size_t packs = features / Pack<T>::N;
+        const int np = packs <= 1024 ? 2 : (packs <= 2048 ? 4 : 8);
+        const size_t smem = 3 * row_bytes;
+        const unsigned pgrid = (unsigned)(samples < (size_t)ctx->num_sms ? samples : (size_t)ctx->num_sms);
+#define SL_PIPE(NPV)                                                                                                   \
+    {                                                                                                                  \
+        auto kern = softmax_pipe_kernel<T, NPV>;                                                                       \
+        SL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        SL_LAUNCH(ctx, kern, pgrid, 512, smem, samples, features, (const T*)x, (T*)out);                               \
+    }
+        if (np == 2) SL_PIPE(2) else if (np == 4) SL_PIPE(4) else SL_PIPE(8)
+#undef SL_PIPE
+        return SL_OK;
+    }
     BlockPlan bp = vec ? plan_block<T>(features, 8) : BlockPlan{0, 0};
     const unsigned grid = (unsigned)(samples < cap * 4 ? samples : cap * 4);
     if (bp.np == 1) SL_LAUNCH(ctx, (softmax_block_kernel<T, 1>), grid, bp.threads, 0, samples, features, (const T*)x, (T*)out);

@@ -17,6 +17,8 @@ Mlp::Mlp(Device& dev, const std::vector<size_t>& dims, LossKind loss) : dev_(dev
         total += round_up(dims[l + 1], 64);
     }
     n_params_ = total;
+    off.push_back(total);
+    seg_off_ = off;  // [W0, b0, W1, b1, ..., end]: layer l owns bucket floats [seg_off_[2l], seg_off_[2l+2])
     params_ = dev_.buffer(total, SL_F32);  // bias = zeros (Matrix::new, nn.rs:33); weights are written by the caller (rand, nn.rs:26)
     bucket_ = dev_.buffer(total, SL_F32);
     bucket_->requires_grad = false;
@@ -146,14 +148,25 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
         const void* lin = li == 0 ? x->dptr : a_[li - 1]->dptr;
         d.check(sl_add_row_mut_grad(c, SL_F32, batch, O, d.grad(layers_[li].bias.data)->dptr, gz_[li]->dptr));   // b.grad += colsum
         d.check(sl_gemm_tn(c, SL_F32, I, O, batch, lin, gz_[li]->dptr, d.grad(layers_[li].weights.data)->dptr, -1));  // Tgemm(k,n,m,lhs,og,W.grad) SET
+        // data-parallel: this layer's gradients are final -> start their sum all-reduce on the communication stream while the
+        // remaining layers' backward gemms keep the tensor cores busy (no-op for a world of one)
+        d.check(sl_allreduce_sum_async(c, SL_F32, (float*)bucket_->dptr + seg_off_[2 * li], seg_off_[2 * li + 2] - seg_off_[2 * li]));
         if (li > 0)
             d.check(sl_linear_bwd_input_relu(c, SL_F32, batch, I, O, layers_[li].weights.data->dptr, gz_[li]->dptr, z_[li - 1]->dptr,
                                              gz_[li - 1]->dptr, -1));
     }
+    exchanged_ = true;
     return read_metrics(want_metrics);
 }
 
-void Mlp::allreduce_grads() { dev_.check(sl_allreduce_sum(dev_.ctx(), SL_F32, bucket_->dptr, n_params_)); }
+void Mlp::allreduce_grads() {
+    if (exchanged_) {  // the fused backward already issued per-layer exchanges: just join the communication stream
+        dev_.check(sl_comm_wait(dev_.ctx()));
+        exchanged_ = false;
+        return;
+    }
+    dev_.check(sl_allreduce_sum(dev_.ctx(), SL_F32, bucket_->dptr, n_params_));
+}
 
 void Mlp::sgd(double lr) {
     // SGD::step over lin1..lin3 params (nn.rs:235-237): parameters and gradients are both flat -> one kernel

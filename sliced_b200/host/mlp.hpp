@@ -82,6 +82,8 @@ class Mlp {
     size_t n_params_ = 0;
     void* metrics_dev_ = nullptr;  // [loss_sum f32][correct i32]
     bool fused_ = false;
+    bool exchanged_ = false;          // per-layer async all-reduces are in flight (fused backward)
+    std::vector<size_t> seg_off_;
     // persistent activations / activation gradients of the fused step (sized for the last batch seen)
     size_t fused_batch_ = 0;
     std::vector<Buf> z_, a_, gz_;
