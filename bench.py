@@ -63,6 +63,18 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
+    of this very command (profiles/r1_ncu_traffic.json, written from the .ncu-rep by tools/ncu_summary.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return dict(bytes_per_launch=d["dram_bytes_per_launch"], unit="B", kernel=d["kernel"], algorithmic_bytes_per_launch=d.get("algorithmic_bytes_per_launch"),
+                    source=d.get("source"))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -72,10 +84,17 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.lines = []
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -84,7 +103,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -94,8 +113,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        # samples that arrived inside the timed region; a region shorter than a few sampling periods (multi-GPU strong scaling:
+        # ~70 ms) falls back to every sample since the sampler started, i.e. warm-up steps (same kernels, same load) + timed region
+        inside = [ln for (t, ln) in self.lines if self.t_begin and self.t_end and self.t_begin <= t <= self.t_end + 0.05]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = [ln for (_, ln) in self.lines]
+            window = "warm-up + timed region (timed region shorter than 3 sampling periods)"
         sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -108,7 +134,9 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), power_w_max=max(pw), samples=len(sm))
+        busy = [c for c, w in zip(sm, pw) if w > 0.5 * max(pw)] or sm   # under load: drop idle samples from before the first kernel
+        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), power_w_max=max(pw), samples=len(busy),
+                    window=window)
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -242,13 +270,14 @@ def run_ours(args):
         return mlp.step(bx, by, bl, batch, LR, grad_rows=global_batch, want_metrics=metrics)
 
     # ---------------- device-resident leg (`value`)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     first_metrics = resident_step(True)
     for _ in range(max(args.warmup, 3) - 1):
         resident_step(True)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     launches0 = dev.launches
     capi.check(ctx, lib.sl_ctx_profile_begin(ctx))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -257,6 +286,7 @@ def run_ours(args):
         resident_step(False)   # loss / accuracy are still computed on the device every step; only the host read is outside `value`
     e1.record(stream)
     torch.cuda.synchronize()
+    sampler.mark_end()
     ms_total = e0.elapsed_time(e1)
     n_l, t_ms, t_fl = C.c_uint64(0), C.c_double(0), C.c_double(0)
     capi.check(ctx, lib.sl_ctx_profile_end(ctx, C.byref(n_l), C.byref(t_ms), C.byref(t_fl)))
@@ -310,7 +340,7 @@ def run_ours(args):
         eff = (t_fl.value / (t_ms.value * 1e-3)) / 1e12 if t_ms.value > 0 else 0.0
         mult = 1 if args.gemm_mode == "tf32" else 3
         roofline = dict(bound="tensor", kernel="gemm_tf32_kernel (tcgen05 kind::tf32, TMA, TMEM)", achieved=eff, peak=tf32_peak, unit="TFLOP/s",
-                        frac=eff / tf32_peak, traffic=None,
+                        frac=eff / tf32_peak, traffic=ncu_traffic(),
                         peak_src=f"{pk['src']}: bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate); kernel timed inside a long step",
                         issued_tflops=eff * mult, pipe_util=eff * mult / tf32_peak,
                         note=f"achieved = algorithmic 2MNK flops of the {n_l.value} tensor-core gemm launches / their summed CUDA-event time "

@@ -141,6 +141,15 @@ int sl_clear(sl_ctx* ctx, void* dst_dev, size_t bytes);
 int sl_fill(sl_ctx* ctx, int dtype, void* dst_dev, double value, size_t n);
 int sl_sync(sl_ctx* ctx);
 
+/* CUDA-graph capture / replay of a sequence of calls on ctx — the device analogue of custos' `Lazy` module building the op
+ * graph once and replaying it with `run()` (ref: examples/sine_net.rs:178-233 `sine_net_lazy2`).  Between begin and end the
+ * calls are recorded, not executed; blocking calls (sl_read, sl_sync, sl_malloc/sl_free) are not allowed, and every buffer /
+ * scratch the sequence needs must already exist (run it once eagerly first).  sl_graph_launch replays on the ctx stream. */
+int sl_graph_begin(sl_ctx* ctx);
+int sl_graph_end(sl_ctx* ctx, void** out_graph_exec);
+int sl_graph_launch(sl_ctx* ctx, void* graph_exec);
+int sl_graph_destroy(sl_ctx* ctx, void* graph_exec);
+
 /* ---------------------------------------------------------------- E: element-wise / broadcast */
 
 /* out[i] = lhs[i] op rhs[i]  (SET).  ref: src/ops2/binary_ew/mod.rs:55-100, cpu_stack.rs:42-54 */

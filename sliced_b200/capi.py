@@ -86,6 +86,10 @@ def _declare(lib):
         "sl_clear": ([_vp, _vp, _sz], _i),
         "sl_fill": ([_vp, _i, _vp, _d, _sz], _i),
         "sl_sync": ([_vp], _i),
+        "sl_graph_begin": ([_vp], _i),
+        "sl_graph_end": ([_vp, P(_vp)], _i),
+        "sl_graph_launch": ([_vp, _vp], _i),
+        "sl_graph_destroy": ([_vp, _vp], _i),
         "sl_binary_ew": ([_vp, _i, _i, _vp, _vp, _vp, _sz], _i),
         "sl_binary_ew_grad": ([_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz], _i),
         "sl_add_ew_grad": ([_vp, _i, _vp, _vp, _vp, _sz], _i),

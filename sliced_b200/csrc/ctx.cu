@@ -260,4 +260,38 @@ int sl_sync(sl_ctx* ctx) {
     return SL_OK;
 }
 
+// ---- CUDA-graph capture / replay of a call sequence (the custos `Lazy` + `run()` seam, examples/sine_net.rs:178-233)
+int sl_graph_begin(sl_ctx* ctx) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    SL_REQUIRE(ctx, !ctx->profiling, "profiling and graph capture are exclusive");
+    SL_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    return SL_OK;
+}
+
+int sl_graph_end(sl_ctx* ctx, void** out_graph_exec) {
+    SL_REQUIRE(ctx, ctx && out_graph_exec, "NULL argument");
+    *out_graph_exec = nullptr;
+    cudaGraph_t g = nullptr;
+    SL_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &g));
+    cudaGraphExec_t ge = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return sl_set_error(ctx, SL_ERR_CUDA, "sl_graph_end: cudaGraphInstantiate -> %s", cudaGetErrorString(e));
+    *out_graph_exec = ge;
+    return SL_OK;
+}
+
+int sl_graph_launch(sl_ctx* ctx, void* graph_exec) {
+    SL_REQUIRE(ctx, ctx && graph_exec, "NULL argument");
+    SL_CUDA(ctx, cudaGraphLaunch((cudaGraphExec_t)graph_exec, ctx->stream));
+    ctx->launches++;
+    return SL_OK;
+}
+
+int sl_graph_destroy(sl_ctx* ctx, void* graph_exec) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (graph_exec) SL_CUDA(ctx, cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return SL_OK;
+}
+
 }  // extern "C"

@@ -170,6 +170,8 @@ struct GemmParams {
     int relu;           // C = (v >= 0) * v after bias
     int c_vec_ok;       // N % 4 == 0 and C 16-byte aligned
     int kc_blocks;      // k-blocks per TMEM accumulation chunk
+    int group;              // tile raster: blocks per group (GROUP_M when 0)
+    int group_along_n;      // group over N (sweep M inside a band of `group` n-blocks) instead of over M
     int splits;             // split-K factor (2-CTA kernel): partial s is written to C + s*M*N, folded afterwards by the host
     float* C2;              // optional second output: C2 = (v >= 0) * v of the value stored to C (fused Matrix::relu)
     const float* mask_src;  // optional [M x N]: v *= (mask_src >= 0) before the store (fused relu gradient)
@@ -274,13 +276,24 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int kc = p.kc_blocks > 0 ? p.kc_blocks : num_kb;
     const int num_chunks = (num_kb + kc - 1) / kc;
     auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
-        const int group_size = GROUP_M * num_n;
-        const int group = tile / group_size;
-        const int first_m = group * GROUP_M;
-        const int gsz = min(num_m - first_m, GROUP_M);
-        const int in_group = tile - group * group_size;
-        m_blk = first_m + in_group % gsz;
-        n_blk = in_group / gsz;
+        // grouped raster: `grp` blocks of the grouped dimension stay L2-resident while the other dimension is swept
+        if (p.group_along_n) {
+            const int group_size = p.group * num_m;
+            const int group = tile / group_size;
+            const int first_n = group * p.group;
+            const int gsz = min(num_n - first_n, p.group);
+            const int in_group = tile - group * group_size;
+            n_blk = first_n + in_group % gsz;
+            m_blk = in_group / gsz;
+        } else {
+            const int group_size = p.group * num_n;
+            const int group = tile / group_size;
+            const int first_m = group * p.group;
+            const int gsz = min(num_m - first_m, p.group);
+            const int in_group = tile - group * group_size;
+            m_blk = first_m + in_group % gsz;
+            n_blk = in_group / gsz;
+        }
     };
 
     if (warp == 0) {
@@ -548,13 +561,24 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
     auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
-        const int group_size = GROUP_M * num_n;
-        const int group = tile / group_size;
-        const int first_m = group * GROUP_M;
-        const int gsz = min(num_m - first_m, GROUP_M);
-        const int in_group = tile - group * group_size;
-        m_blk = first_m + in_group % gsz;
-        n_blk = in_group / gsz;
+        // grouped raster: `grp` blocks of the grouped dimension stay L2-resident while the other dimension is swept
+        if (p.group_along_n) {
+            const int group_size = p.group * num_m;
+            const int group = tile / group_size;
+            const int first_n = group * p.group;
+            const int gsz = min(num_n - first_n, p.group);
+            const int in_group = tile - group * group_size;
+            n_blk = first_n + in_group % gsz;
+            m_blk = in_group / gsz;
+        } else {
+            const int group_size = p.group * num_n;
+            const int group = tile / group_size;
+            const int first_m = group * p.group;
+            const int gsz = min(num_m - first_m, p.group);
+            const int in_group = tile - group * group_size;
+            m_blk = first_m + in_group % gsz;
+            n_blk = in_group / gsz;
+        }
     };
 
     if (warp == 0) {
@@ -926,6 +950,9 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const
         cfg = (M >= 256 && N >= 256 && pair_tiles >= ctx->num_sms / 4) ? 4 : 3;   // enough 256x256 tiles to occupy half the CTA pairs
     }
     p.splits = 1;
+    p.group = env_int("SLICED_GEMM_GROUP", GROUP_M);
+    p.group_along_n = env_int("SLICED_GEMM_GROUP_N", 0);
+    if (p.group < 1) p.group = 1;
     if (cfg == 4) {  // cta_group::2, 256x256 tile per CTA pair
         // Wave quantisation: with T tiles on 74 CTA pairs the last wave is T mod 74 wide (dW of the MLP: 256 tiles = 3.46 waves
         // -> 4).  When that wastes > 8 % and K is long, split K so that tiles x splits fills whole waves; the partial tiles go

@@ -71,6 +71,7 @@ def _lib():
             "slh_mlp_allreduce_grads": ([_vp], _i),
             "slh_mlp_sgd": ([_vp, _d], _i),
             "slh_mlp_step": ([_vp, _vp, _vp, _vp, _sz, _sz, _d, _i, P(_d), P(C.c_longlong)], _i),
+            "slh_mlp_step_replay": ([_vp, _vp, _vp, _vp, _sz, _sz, _d, _i, P(_d), P(C.c_longlong)], _i),
             "slh_mlp_predict": ([_vp, _vp, _sz], _vp),
         }
         for name, (args, res) in sig.items():
@@ -330,6 +331,13 @@ class Mlp:
         loss, correct = _d(0), C.c_longlong(0)
         _chk(_lib().slh_mlp_step(self.h, x.h, y.h, labels.h if labels else None, batch, grad_rows or batch, lr, int(want_metrics),
                                  C.byref(loss), C.byref(correct)))
+        return loss.value, correct.value
+
+    def step_replay(self, x, y, labels, batch, lr, grad_rows=None, want_metrics=True):
+        """The step as a CUDA graph: recorded on the first call, one cudaGraphLaunch afterwards (custos `Lazy` + `run()`)."""
+        loss, correct = _d(0), C.c_longlong(0)
+        _chk(_lib().slh_mlp_step_replay(self.h, x.h, y.h, labels.h if labels else None, batch, grad_rows or batch, lr, int(want_metrics),
+                                        C.byref(loss), C.byref(correct)))
         return loss.value, correct.value
 
     def predict(self, x: Buffer, batch: int) -> Buffer:

@@ -184,6 +184,16 @@ int slh_mlp_step(slh_mlp* m, slh_buffer* x, slh_buffer* y, slh_buffer* labels, s
         return 0;
     }, -1);
 }
+int slh_mlp_step_replay(slh_mlp* m, slh_buffer* x, slh_buffer* y, slh_buffer* labels, size_t batch, size_t grad_rows, double lr, int want_metrics,
+                        double* loss_sum, long long* correct) {
+    return guard([&]() {
+        StepResult r = ((Mlp*)m)->step_replay(((BufHandle*)x)->b, ((BufHandle*)y)->b, labels ? ((BufHandle*)labels)->b : Buf(), batch, grad_rows, lr,
+                                              want_metrics != 0);
+        if (loss_sum) *loss_sum = r.loss_sum;
+        if (correct) *correct = r.correct;
+        return 0;
+    }, -1);
+}
 slh_buffer* slh_mlp_predict(slh_mlp* m, slh_buffer* x, size_t batch) {
     return guard([&]() { return (slh_buffer*)wrap_handle(((Mlp*)m)->predict(((BufHandle*)x)->b, batch).data); }, (slh_buffer*)nullptr);
 }

@@ -37,7 +37,35 @@ Mlp::Mlp(Device& dev, const std::vector<size_t>& dims, LossKind loss) : dev_(dev
 }
 
 Mlp::~Mlp() {
+    if (graph_) sl_graph_destroy(dev_.ctx(), graph_);
     if (metrics_dev_) sl_free(dev_.ctx(), metrics_dev_);
+}
+
+StepResult Mlp::step_replay(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, double lr, bool want_metrics) {
+    const GraphKey key{x->dptr, y->dptr, labels ? labels->dptr : nullptr, batch, grad_rows, lr, fused_};
+    const bool same = graph_ && key.x == gkey_.x && key.y == gkey_.y && key.l == gkey_.l && key.batch == gkey_.batch &&
+                      key.rows == gkey_.rows && key.lr == gkey_.lr && key.fused == gkey_.fused;
+    if (same) {
+        dev_.check(sl_graph_launch(dev_.ctx(), graph_));
+        return read_metrics(want_metrics);
+    }
+    if (graph_) {
+        dev_.check(sl_graph_destroy(dev_.ctx(), graph_));
+        graph_ = nullptr;
+    }
+    StepResult r = step(x, y, labels, batch, grad_rows, lr, want_metrics);   // this call's step, eagerly (creates every buffer)
+    dev_.check(sl_graph_begin(dev_.ctx()));
+    try {
+        step(x, y, labels, batch, grad_rows, lr, false);                     // recorded, not executed
+    } catch (...) {
+        void* g = nullptr;
+        sl_graph_end(dev_.ctx(), &g);
+        if (g) sl_graph_destroy(dev_.ctx(), g);
+        throw;
+    }
+    dev_.check(sl_graph_end(dev_.ctx(), &graph_));
+    gkey_ = key;
+    return r;
 }
 
 StepResult Mlp::forward_backward(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics) {

@@ -70,6 +70,10 @@ class Mlp {
         sgd(lr);
         return r;
     }
+    // The same step recorded once as a CUDA graph and replayed (custos `Lazy` + `run()`, examples/sine_net.rs:178-233): for the
+    // launch-latency-bound shipped sizes (1000 x 64 matrices, ~60 kernels per step).  The first call runs eagerly (and allocates
+    // every buffer), records the graph, later calls with the same buffers / sizes / lr are one cudaGraphLaunch.
+    StepResult step_replay(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, double lr, bool want_metrics);
     Matrix predict(const Buf& x, size_t batch);  // forward only, tape disabled
 
   private:
@@ -83,6 +87,8 @@ class Mlp {
     void* metrics_dev_ = nullptr;  // [loss_sum f32][correct i32]
     bool fused_ = false;
     bool exchanged_ = false;          // per-layer async all-reduces are in flight (fused backward)
+    void* graph_ = nullptr;           // captured step (step_replay)
+    struct GraphKey { const void *x, *y, *l; size_t batch, rows; double lr; bool fused; } gkey_{};
     std::vector<size_t> seg_off_;
     // persistent activations / activation gradients of the fused step (sized for the last batch seen)
     size_t fused_batch_ = 0;
