@@ -222,6 +222,14 @@ int sl_gemm_ex(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_
 int sl_gemm_grad(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs,
                  void* lhs_grad, void* rhs_grad, const void* out_grad, int accumulate, int mode);
 
+/* Operand-plane reuse scope for the tensor-core gemm.  Every f32 gemm first derives TF32 hi/lo planes from its operands; between
+ * begin and end those planes are kept and reused by later gemms that read the SAME buffer (same pointer and size) — e.g. an
+ * activation in its forward gemm and again in the weight-gradient gemm of the same training step.  Contract: a buffer that has
+ * been read by a gemm inside the scope is not modified by anything but a gemm of this library until the scope ends (a gemm
+ * that overwrites it invalidates its planes).  sl_gemm_grad opens an implicit scope around its two gemms (both read out_grad). */
+int sl_gemm_scope_begin(sl_ctx* ctx);
+int sl_gemm_scope_end(sl_ctx* ctx);
+
 /* Fused Linear forward — examples/nn.rs:38-46 (`gemm` + `add_row_mut`) followed by `Matrix::relu` (src/matrix.rs:169-190) in the gemm
  * epilogue:  z[m x n] = lhs[m x k] * rhs[k x n] + bias[n];  if act_out != NULL: act_out = (z >= 0) * z.   bias may be NULL.
  * Bit-identical to sl_gemm + sl_add_row_mut + sl_unary(SL_UN_RELU): the same per-element operations in the same order. f32. */

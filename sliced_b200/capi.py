@@ -111,6 +111,8 @@ def _declare(lib):
         "sl_gemm_tn": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _i], _i),
         "sl_gemm_ex": ([_vp, _i, _i, _i, _sz, _sz, _sz, _vp, _vp, _vp, _i, _i], _i),
         "sl_gemm_grad": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _i, _i], _i),
+        "sl_gemm_scope_begin": ([_vp], _i),
+        "sl_gemm_scope_end": ([_vp], _i),
         "sl_linear_fwd": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _i], _i),
         "sl_linear_bwd_input_relu": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _i], _i),
         "sl_sum": ([_vp, _i, _vp, _sz, _vp], _i),

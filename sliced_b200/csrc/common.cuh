@@ -28,6 +28,11 @@ struct sl_ctx {
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; double flops; };
     std::vector<ProfRec> prof;
+    // operand-plane reuse (sl_gemm_scope_begin / _end): hi/lo TF32 planes of gemm operands kept for later gemms on the same buffer
+    struct PlaneEntry { const void* src; size_t elems; float* hi; float* lo; size_t cap_bytes; bool valid; };
+    std::vector<PlaneEntry> plane_cache;
+    size_t plane_cursor = 0;
+    bool plane_scope = false;
     // second stream for host->device prefetch (sl_write_prefetch), created lazily
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_done = nullptr, compute_done = nullptr;

@@ -103,6 +103,10 @@ int sl_ctx_destroy(sl_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     sl_comm_destroy(ctx);
+    for (auto& e : ctx->plane_cache) {
+        if (e.hi) cudaFree(e.hi);
+        if (e.lo) cudaFree(e.lo);
+    }
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ws2) cudaFree(ctx->ws2);
     if (ctx->copy_stream) {

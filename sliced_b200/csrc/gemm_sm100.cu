@@ -142,9 +142,28 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= layout << 61;
     return d;
 }
-// Instruction descriptor: D = F32 (bits[4,6)=1), A = B = TF32 (bits[7,10)=2, [10,13)=2), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operand tile [BLOCK_K x 128 mn] fp32 (the contraction index is the SLOW one in memory: gemm's rhs, Tgemm's operands):
+// four 32-mn chunks, each written by its own TMA box {32 mn, BLOCK_K k} as BLOCK_K rows of 128 bytes.  For 32-bit MN-major
+// operands the tensor core only accepts the "128B swizzle with 32-byte atoms" layout (UMMA layout type 1, TMA
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): within every group of 4 k-rows the 32-byte chunks of a row are XOR-ed with the row
+// index (address bits [5,7) ^= bits [7,9)).  Canonical form ((T,8,m),(4,k)) : ((1,T,LBO),(8T,SBO)), T = 4 tf32 per 16 B:
+// LBO = distance between 32-mn chunks, SBO = distance between groups of 4 k-rows (512 B).  One MMA (K = 8) consumes two
+// such groups (1024 B) of every chunk.
+template <int BLOCK_K>
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((BLOCK_K * 128) >> 4) << 16;   // LBO: one chunk = BLOCK_K rows x 128 B
+    d |= (uint64_t)(512 >> 4) << 32;               // SBO: 4 k-rows x 128 B
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                        // SWIZZLE_128B_BASE32B
+    return d;
+}
+// Instruction descriptor: D = F32 (bits[4,6)=1), A = B = TF32 (bits[7,10)=2, [10,13)=2), A / B major (bit 15 / 16: 0 = K-major,
+// 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------ the MMA kernel
@@ -502,7 +521,7 @@ struct Gemm2Cfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "stage ring does not fit in shared memory");
 };
 
-template <int TERMS, int STAGES>
+template <int TERMS, int STAGES, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
@@ -598,11 +617,20 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                     const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
                     const uint32_t fb = mapa_shared(full_bar(stage), 0);  // the leader's barrier, as a shared::cluster address
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-                    tma_load_2d_2sm(sa, &map_a_hi, fb, kb * BLOCK_K, row_a);
-                    tma_load_2d_2sm(sb, &map_b_hi, fb, kb * BLOCK_K, row_b);
+                    // K-major plane: one box {BLOCK_K k, 128 rows}; MN-major plane: four boxes {32 mn, BLOCK_K k}, one per 32-mn chunk
+                    auto load_plane = [&](uint32_t dst, const CUtensorMap* map, int row0, bool mn) {
+                        if (!mn) {
+                            tma_load_2d_2sm(dst, map, fb, kb * BLOCK_K, row0);
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) tma_load_2d_2sm(dst + g * (BLOCK_K * 128), map, fb, row0 + g * 32, kb * BLOCK_K);
+                        }
+                    };
+                    load_plane(sa, &map_a_hi, row_a, A_MN);
+                    load_plane(sb, &map_b_hi, row_b, B_MN);
                     if (TERMS == 3) {
-                        tma_load_2d_2sm(sa + Cfg::A_BYTES, &map_a_lo, fb, kb * BLOCK_K, row_a);
-                        tma_load_2d_2sm(sb + Cfg::B_BYTES, &map_b_lo, fb, kb * BLOCK_K, row_b);
+                        load_plane(sa + Cfg::A_BYTES, &map_a_lo, row_a, A_MN);
+                        load_plane(sb + Cfg::B_BYTES, &map_b_lo, row_b, B_MN);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -615,7 +643,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     } else if (warp == 1) {
         // ================================================================= MMA issuer (leader CTA only)
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(Cfg::TILE_M, Cfg::TILE_N);
+            constexpr uint32_t idesc = make_idesc_tf32(Cfg::TILE_M, Cfg::TILE_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             uint32_t g = 0;
@@ -634,20 +662,22 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                         tc_fence_after();
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                         const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
-                        const uint64_t da_hi = make_smem_desc<BLOCK_K>(sa);
-                        const uint64_t db_hi = make_smem_desc<BLOCK_K>(sb);
-                        const uint64_t da_lo = make_smem_desc<BLOCK_K>(sa + Cfg::A_BYTES);
-                        const uint64_t db_lo = make_smem_desc<BLOCK_K>(sb + Cfg::B_BYTES);
+                        const uint64_t da_hi = A_MN ? make_smem_desc_mn<BLOCK_K>(sa) : make_smem_desc<BLOCK_K>(sa);
+                        const uint64_t db_hi = B_MN ? make_smem_desc_mn<BLOCK_K>(sb) : make_smem_desc<BLOCK_K>(sb);
+                        const uint64_t da_lo = A_MN ? make_smem_desc_mn<BLOCK_K>(sa + Cfg::A_BYTES) : make_smem_desc<BLOCK_K>(sa + Cfg::A_BYTES);
+                        const uint64_t db_lo = B_MN ? make_smem_desc_mn<BLOCK_K>(sb + Cfg::B_BYTES) : make_smem_desc<BLOCK_K>(sb + Cfg::B_BYTES);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            // one k-slice (8 k): K-major -> 32 bytes further along the 128-byte row; MN-major -> the next 8-row group (1024 B)
+                            const uint64_t koff_a = (uint64_t)((A_MN ? k * 1024 : k * UMMA_K * 4) >> 4);
+                            const uint64_t koff_b = (uint64_t)((B_MN ? k * 1024 : k * UMMA_K * 4) >> 4);
                             const uint32_t first = (kb == kb_begin && k == 0) ? 0u : 1u;
                             if (TERMS == 3) {
-                                umma_tf32_2sm(tmem_d, da_lo + koff, db_hi + koff, idesc, first);
-                                umma_tf32_2sm(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
-                                umma_tf32_2sm(tmem_d, da_hi + koff, db_hi + koff, idesc, 1u);
+                                umma_tf32_2sm(tmem_d, da_lo + koff_a, db_hi + koff_b, idesc, first);
+                                umma_tf32_2sm(tmem_d, da_hi + koff_a, db_lo + koff_b, idesc, 1u);
+                                umma_tf32_2sm(tmem_d, da_hi + koff_a, db_hi + koff_b, idesc, 1u);
                             } else {
-                                umma_tf32_2sm(tmem_d, da_hi + koff, db_hi + koff, idesc, first);
+                                umma_tf32_2sm(tmem_d, da_hi + koff_a, db_hi + koff_b, idesc, first);
                             }
                         }
                         umma_commit_2sm(empty_bar(stage), 0x3);   // frees the stage in BOTH CTAs
@@ -873,21 +903,38 @@ static int launch_cfg(sl_ctx* ctx, const GemmParams& p, const float* a_hi, const
 }
 
 // 2-CTA (cta_group::2) launch: clusters of 2 CTAs, one 256x256 tile per cluster; each CTA's TMA box is 128 rows of A / of B
-template <int TERMS, int STAGES>
+// MN-major plane: stored [K x rows] with leading dimension ld (rows contiguous); box = 32 rows(mn) x BLOCK_K k
+static int make_map_mn(sl_ctx* ctx, CUtensorMap* map, const float* base, size_t rows, size_t K, size_t ld, int block_k) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return sl_set_error(ctx, SL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)K};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)block_k};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sl_set_error(ctx, SL_ERR_CUDA, "cuTensorMapEncodeTiled (MN-major) failed (%d) rows=%zu K=%zu ld=%zu", (int)r, rows, K, ld);
+    return SL_OK;
+}
+
+template <int TERMS, int STAGES, bool A_MN, bool B_MN>
 static int launch_cfg_2cta(sl_ctx* ctx, const GemmParams& p, const float* a_hi, const float* a_lo, size_t lda, const float* b_hi,
                            const float* b_lo, size_t ldb) {
     using Cfg = Gemm2Cfg<TERMS, STAGES>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_map(ctx, &ma_hi, a_hi, p.M, p.K, lda, Cfg::BLOCK_K, 128)) != SL_OK) return rc;
-    if ((rc = make_map(ctx, &mb_hi, b_hi, p.N, p.K, ldb, Cfg::BLOCK_K, 128)) != SL_OK) return rc;
+    auto mk = [&](CUtensorMap* m, const float* base, size_t rows, size_t ld, bool mn) {
+        return mn ? make_map_mn(ctx, m, base, rows, p.K, ld, Cfg::BLOCK_K) : make_map(ctx, m, base, rows, p.K, ld, Cfg::BLOCK_K, 128);
+    };
+    if ((rc = mk(&ma_hi, a_hi, p.M, lda, A_MN)) != SL_OK) return rc;
+    if ((rc = mk(&mb_hi, b_hi, p.N, ldb, B_MN)) != SL_OK) return rc;
     ma_lo = ma_hi;
     mb_lo = mb_hi;
     if (TERMS == 3) {
-        if ((rc = make_map(ctx, &ma_lo, a_lo, p.M, p.K, lda, Cfg::BLOCK_K, 128)) != SL_OK) return rc;
-        if ((rc = make_map(ctx, &mb_lo, b_lo, p.N, p.K, ldb, Cfg::BLOCK_K, 128)) != SL_OK) return rc;
+        if ((rc = mk(&ma_lo, a_lo, p.M, lda, A_MN)) != SL_OK) return rc;
+        if ((rc = mk(&mb_lo, b_lo, p.N, ldb, B_MN)) != SL_OK) return rc;
     }
-    auto kern = gemm_tf32_2cta_kernel<TERMS, STAGES>;
+    auto kern = gemm_tf32_2cta_kernel<TERMS, STAGES, A_MN, B_MN>;
     SL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int num_tiles = ((p.M + Cfg::TILE_M - 1) / Cfg::TILE_M) * ((p.N + Cfg::TILE_N - 1) / Cfg::TILE_N);
     const int max_clusters = ctx->num_sms / 2;
@@ -917,6 +964,16 @@ static int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+// tile configuration: SLICED_GEMM_CFG = 0 auto | 1: 128x256x32 | 2: 128x256x16 | 3: 128x128x32 | 4: 2-CTA pairs, 256x256x32 per pair
+static int sl_gemm_pick_cfg(sl_ctx* ctx, size_t M, size_t N) {
+    int cfg = env_int("SLICED_GEMM_CFG", 0);
+    if (cfg == 0) {
+        const long pair_tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
+        cfg = (M >= 256 && N >= 256 && pair_tiles >= ctx->num_sms / 4) ? 4 : 3;   // enough 256x256 tiles to occupy half the CTA pairs
+    }
+    return cfg;
+}
+
 // folds split-K partials in split order and applies the epilogue (see sl_gemm_tc_planes)
 __global__ void __launch_bounds__(256) splitk_fold_kernel(size_t total, size_t n, int splits, const float* __restrict__ partial, float* C, int accumulate,
                                                           const float* __restrict__ bias, int relu, float* C2, const float* __restrict__ mask_src) {
@@ -935,7 +992,7 @@ __global__ void __launch_bounds__(256) splitk_fold_kernel(size_t total, size_t n
 // Runs the tensor-core kernel on prepared K-major planes: C[M x N] (=|+=) A[M x K] * B[N x K]^T (+ bias, relu).
 // a_lo / b_lo are NULL in TF32 mode.  lda / ldb in floats, multiples of 4, planes 16-byte aligned.
 int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const float* a_lo, size_t lda, const float* b_hi, const float* b_lo,
-                      size_t ldb, float* C, const float* bias, int accumulate, int relu, float* c2, const float* mask_src) {
+                      size_t ldb, float* C, const float* bias, int accumulate, int relu, float* c2, const float* mask_src, int a_mn, int b_mn) {
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu; p.C2 = c2; p.mask_src = mask_src;
     p.c_vec_ok = (N % 4 == 0) && sl_aligned16(C) && (!bias || sl_aligned16(bias)) && (!c2 || sl_aligned16(c2)) && (!mask_src || sl_aligned16(mask_src));
@@ -944,14 +1001,14 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const
     p.kc_blocks = three ? env_int("SLICED_GEMM_KC", 4) : env_int("SLICED_GEMM_KC_TF32", 0);
     // tile configuration: SLICED_GEMM_CFG = 0 auto | 1: 128x256x32 | 2: 128x256x16 (swizzle 64B, deeper ring) | 3: 128x128x32
     //                                       | 4: 2-CTA pairs (cta_group::2), 256x256x32 per pair
-    int cfg = env_int("SLICED_GEMM_CFG", 0);
-    if (cfg == 0) {
-        const long pair_tiles = (long)((M + 255) / 256) * ((N + 255) / 256);
-        cfg = (M >= 256 && N >= 256 && pair_tiles >= ctx->num_sms / 4) ? 4 : 3;   // enough 256x256 tiles to occupy half the CTA pairs
-    }
+    const int cfg = sl_gemm_pick_cfg(ctx, M, N);
+    if (cfg != 4 && (a_mn || b_mn)) return sl_set_error(ctx, SL_ERR_INVALID_ARG, "MN-major planes need the 2-CTA kernel");
     p.splits = 1;
-    p.group = env_int("SLICED_GEMM_GROUP", GROUP_M);
-    p.group_along_n = env_int("SLICED_GEMM_GROUP_N", 0);
+    // Tile raster.  Measured on the MLP shapes (tools/raster_sweep.py): narrow groups win — with 2 blocks of the LONG dimension per
+    // group the tiles running concurrently span the whole short dimension, so the smaller operand (the weights: 134 MB of hi/lo
+    // planes, about one L2) is shared by every CTA pair while the big operand streams through exactly once.
+    p.group = env_int("SLICED_GEMM_GROUP", 2);
+    p.group_along_n = env_int("SLICED_GEMM_GROUP_N", N > M ? 1 : 0);
     if (p.group < 1) p.group = 1;
     if (cfg == 4) {  // cta_group::2, 256x256 tile per CTA pair
         // Wave quantisation: with T tiles on 74 CTA pairs the last wave is T mod 74 wide (dW of the MLP: 256 tiles = 3.46 waves
@@ -980,7 +1037,14 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const
             q.bias = nullptr; q.accumulate = 0; q.relu = 0; q.C2 = nullptr; q.mask_src = nullptr;
             q.c_vec_ok = (N % 4 == 0);
         }
-        int rc = three ? launch_cfg_2cta<3, 3>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb) : launch_cfg_2cta<1, 6>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        int rc;
+#define SL_2CTA(AM, BM) (three ? launch_cfg_2cta<3, 3, AM, BM>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb) \
+                               : launch_cfg_2cta<1, 6, AM, BM>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb))
+        if (a_mn && b_mn) rc = SL_2CTA(true, true);
+        else if (a_mn) rc = SL_2CTA(true, false);
+        else if (b_mn) rc = SL_2CTA(false, true);
+        else rc = SL_2CTA(false, false);
+#undef SL_2CTA
         if (rc != SL_OK || best == 1) return rc;
         const size_t total = (size_t)M * N;
         const size_t cap = (size_t)ctx->num_sms * 8;
@@ -1024,6 +1088,34 @@ static bool tc_eligible(size_t m, size_t n, size_t k) {
     return m >= min_dim && n >= min_dim && k >= 32 && (double)m * (double)n * (double)k >= (double)(1 << 22);
 }
 
+// ---- operand-plane reuse.  Inside a scope (sl_gemm_scope_begin/_end) the planes of an operand that is split "flat" (same
+// layout as the source: K-major with K % 4 == 0, or MN-major) are kept in their own allocation and reused by every later gemm of
+// the scope that reads the same buffer: out_grad in both halves of gemm_grad, an activation in its forward gemm and in the
+// weight-gradient gemm, a weight in forward and in the input-gradient gemm.  Slots are handed out in call order, so a loop
+// that issues the same sequence every iteration never reallocates.
+static int plane_cache_get(sl_ctx* ctx, const float* src, size_t elems, bool three, float** hi, float** lo, bool* hit) {
+    for (auto& e : ctx->plane_cache)
+        if (e.valid && e.src == src && e.elems == elems && (!three || e.lo)) {
+            *hi = e.hi; *lo = three ? e.lo : nullptr; *hit = true;
+            return SL_OK;
+        }
+    if (ctx->plane_cursor >= ctx->plane_cache.size()) ctx->plane_cache.push_back(sl_ctx::PlaneEntry{nullptr, 0, nullptr, nullptr, 0, false});
+    sl_ctx::PlaneEntry& e = ctx->plane_cache[ctx->plane_cursor++];
+    const size_t bytes = ((elems * 4) + 255) & ~size_t(255);
+    if (e.cap_bytes < bytes || (three && !e.lo)) {
+        SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (e.hi) cudaFree(e.hi);
+        if (e.lo) cudaFree(e.lo);
+        e.hi = e.lo = nullptr;
+        SL_CUDA(ctx, cudaMalloc((void**)&e.hi, bytes));
+        if (three) SL_CUDA(ctx, cudaMalloc((void**)&e.lo, bytes));
+        e.cap_bytes = bytes;
+    }
+    e.src = src; e.elems = elems; e.valid = true;
+    *hi = e.hi; *lo = three ? e.lo : nullptr; *hit = false;
+    return SL_OK;
+}
+
 // fused epilogue request (f32): v = acc (+ C) (+ bias[n]) ; v *= (mask_src >= 0) ; [relu in place] ; C = v ; C2 = relu(v)
 struct Epi {
     const float* bias = nullptr;
@@ -1056,6 +1148,10 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
     if (k == 0) return accumulate ? SL_OK : sl_clear(ctx, c, m * n * sl_dtype_size(dtype));
     SL_REQUIRE(ctx, a && b, "NULL operand");
     if (mode < 0) mode = ctx->gemm_mode;
+    // a gemm that overwrites a buffer whose planes are cached makes them stale
+    if (ctx->plane_scope)
+        for (auto& e : ctx->plane_cache)
+            if (e.valid && (e.src == c || e.src == (const void*)epi.c2)) e.valid = false;
     if (dtype != SL_F32 || mode == SL_GEMM_SIMT || !tc_eligible(m, n, k)) {
         if (epi.any() && dtype != SL_F32) return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "fused epilogue is f32 only");
         int rc = 1;
@@ -1070,38 +1166,67 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
         return SL_OK;
     }
     const bool three = mode == SL_GEMM_3XTF32;
-    const size_t ldp = (k + 3) & ~size_t(3);
-    // A operand: contraction index contiguous iff !trans_a ; B operand ([N x K] wanted): contiguous iff trans_b
-    const bool a_direct = !three && !trans_a && (k % 4 == 0) && sl_aligned16(a);
-    const bool b_direct = !three && trans_b && (k % 4 == 0) && sl_aligned16(b);
-    const size_t a_plane = ((m * ldp * 4) + 255) & ~size_t(255);
-    const size_t b_plane = ((n * ldp * 4) + 255) & ~size_t(255);
-    const size_t need = (a_direct ? 0 : a_plane * (three ? 2 : 1)) + (b_direct ? 0 : b_plane * (three ? 2 : 1));
+    // Operand forms.  K-major = contraction index contiguous (A: !trans_a, B: trans_b).  The 2-CTA kernel also consumes MN-major
+    // operands directly (UMMA MN-major descriptors), so a non-K-contiguous operand is only SPLIT in place there; the single-CTA
+    // kernels want K-major tiles and get a transposing split.
+    const bool mn_ok = sl_gemm_pick_cfg(ctx, m, n) == 4 && !env_int("SLICED_GEMM_NO_MN", 0);
+    const bool a_kc = !trans_a, b_kc = trans_b != 0;
+    const bool a_mn = !a_kc && mn_ok && (m % 4 == 0), b_mn = !b_kc && mn_ok && (n % 4 == 0);
+    // leading dimensions of the planes: K-major [rows x ldk], MN-major [k x ldm]
+    const size_t ldk = (k + 3) & ~size_t(3);
+    const size_t a_ld = a_mn ? m : ldk, b_ld = b_mn ? n : ldk;
+    const size_t a_elems = a_mn ? k * m : m * ldk, b_elems = b_mn ? k * n : n * ldk;
+    const bool a_direct = !three && (a_kc ? (k % 4 == 0) : a_mn) && sl_aligned16(a);
+    const bool b_direct = !three && (b_kc ? (k % 4 == 0) : b_mn) && sl_aligned16(b);
+    const size_t a_plane = ((a_elems * 4) + 255) & ~size_t(255);
+    const size_t b_plane = ((b_elems * 4) + 255) & ~size_t(255);
+    // flat split (planes laid out exactly like the source buffer) -> eligible for reuse inside a scope
+    const bool a_cacheable = ctx->plane_scope && !a_direct && (a_mn || (a_kc && ldk == k));
+    const bool b_cacheable = ctx->plane_scope && !b_direct && (b_mn || (b_kc && ldk == k));
+    const size_t need = ((a_direct || a_cacheable) ? 0 : a_plane * (three ? 2 : 1)) + ((b_direct || b_cacheable) ? 0 : b_plane * (three ? 2 : 1));
     char* ws = nullptr;
     if (need) {
         int rc = sl_ws2_reserve(ctx, need, (void**)&ws);
         if (rc != SL_OK) return rc;
     }
     const float *a_hi = (const float*)a, *a_lo = nullptr, *b_hi = (const float*)b, *b_lo = nullptr;
-    size_t lda = k, ldb = k;
+    size_t lda = a_kc ? k : m, ldb = b_kc ? k : n;
     char* cur = ws;
     if (!a_direct) {
-        float* h = (float*)cur; cur += a_plane;
-        float* l = nullptr;
-        if (three) { l = (float*)cur; cur += a_plane; }
-        int rc = sl_gemm_prep_operand(ctx, (const float*)a, m, k, !trans_a, h, l, ldp);
-        if (rc != SL_OK) return rc;
-        a_hi = h; a_lo = l; lda = ldp;
+        float *h, *l = nullptr;
+        bool hit = false;
+        if (a_cacheable) {
+            int rc = plane_cache_get(ctx, (const float*)a, m * k, three, &h, &l, &hit);
+            if (rc != SL_OK) return rc;
+        } else {
+            h = (float*)cur; cur += a_plane;
+            if (three) { l = (float*)cur; cur += a_plane; }
+        }
+        // MN-major: the source [k x m] is split element-wise as a [k x m] matrix; K-major: split (a_kc) or transpose-split
+        if (!hit) {
+            int rc = a_mn ? sl_gemm_prep_operand(ctx, (const float*)a, k, m, 1, h, l, a_ld) : sl_gemm_prep_operand(ctx, (const float*)a, m, k, a_kc, h, l, a_ld);
+            if (rc != SL_OK) return rc;
+        }
+        a_hi = h; a_lo = l; lda = a_ld;
     }
     if (!b_direct) {
-        float* h = (float*)cur; cur += b_plane;
-        float* l = nullptr;
-        if (three) { l = (float*)cur; cur += b_plane; }
-        int rc = sl_gemm_prep_operand(ctx, (const float*)b, n, k, trans_b, h, l, ldp);
-        if (rc != SL_OK) return rc;
-        b_hi = h; b_lo = l; ldb = ldp;
+        float *h, *l = nullptr;
+        bool hit = false;
+        if (b_cacheable) {
+            int rc = plane_cache_get(ctx, (const float*)b, n * k, three, &h, &l, &hit);
+            if (rc != SL_OK) return rc;
+        } else {
+            h = (float*)cur; cur += b_plane;
+            if (three) { l = (float*)cur; cur += b_plane; }
+        }
+        if (!hit) {
+            int rc = b_mn ? sl_gemm_prep_operand(ctx, (const float*)b, k, n, 1, h, l, b_ld) : sl_gemm_prep_operand(ctx, (const float*)b, n, k, b_kc, h, l, b_ld);
+            if (rc != SL_OK) return rc;
+        }
+        b_hi = h; b_lo = l; ldb = b_ld;
     }
-    return sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, lda, b_hi, b_lo, ldb, (float*)c, bias, accumulate, relu, epi.c2, epi.mask_src);
+    return sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, lda, b_hi, b_lo, ldb, (float*)c, bias, accumulate, relu, epi.c2, epi.mask_src,
+                             a_mn ? 1 : 0, b_mn ? 1 : 0);
 }
 
 extern "C" {
@@ -1145,10 +1270,31 @@ int sl_linear_bwd_input_relu(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t 
     return gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, x_grad, 0, mode, e);
 }
 
+int sl_gemm_scope_begin(sl_ctx* ctx) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    for (auto& e : ctx->plane_cache) e.valid = false;
+    ctx->plane_cursor = 0;
+    ctx->plane_scope = true;
+    return SL_OK;
+}
+
+int sl_gemm_scope_end(sl_ctx* ctx) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    for (auto& e : ctx->plane_cache) e.valid = false;
+    ctx->plane_scope = false;
+    return SL_OK;
+}
+
 int sl_gemm_grad(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, void* lhs_grad, void* rhs_grad,
                  const void* out_grad, int accumulate, int mode) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     SL_REQUIRE(ctx, out_grad != nullptr || m == 0 || n == 0, "NULL out_grad");
+    // both halves read out_grad: split it once (implicit scope unless the caller already opened one)
+    struct ScopeGuard {
+        sl_ctx* c; bool own;
+        ScopeGuard(sl_ctx* ctx, bool want) : c(ctx), own(want && !ctx->plane_scope) { if (own) sl_gemm_scope_begin(c); }
+        ~ScopeGuard() { if (own) sl_gemm_scope_end(c); }
+    } guard(ctx, lhs_grad && rhs_grad && dtype == SL_F32);
     if (lhs_grad) {  // gemmT(m, k, n, out_grad, rhs, lhs_grad): lhs_grad[m x k] = out_grad[m x n] * rhs[k x n]^T
         int rc = gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, lhs_grad, accumulate, mode, Epi{});
         if (rc != SL_OK) return rc;

@@ -147,6 +147,9 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
     // parameter gradients accumulate (bias: += column sums) -> zero the bucket; activation gradients are all SET
     d.check(sl_clear(c, bucket_->dptr, bucket_->bytes()));
     d.check(sl_clear(c, metrics_dev_, 16));
+    // every activation / weight / gz buffer is read by two gemms of this step (forward + a gradient gemm): split each into its
+    // TF32 planes once.  Nothing but gemms writes those buffers between here and the end of the backward pass.
+    d.check(sl_gemm_scope_begin(c));
 
     // ---- forward: Linear + relu fused; the 10-class head goes through the skinny kernel + add_row_mut + softmax
     const void* in = x->dptr;
@@ -183,6 +186,7 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
             d.check(sl_linear_bwd_input_relu(c, SL_F32, batch, I, O, layers_[li].weights.data->dptr, gz_[li]->dptr, z_[li - 1]->dptr,
                                              gz_[li - 1]->dptr, -1));
     }
+    d.check(sl_gemm_scope_end(c));
     exchanged_ = true;
     return read_metrics(want_metrics);
 }

@@ -232,6 +232,12 @@ class Context:
         self._c(self.lib.sl_gemm_grad(self.h, out_grad.code, m, k, n, lhs.ptr, rhs.ptr, self._p(lhs_grad), self._p(rhs_grad), out_grad.ptr,
                                       int(accumulate), mode))
 
+    def gemm_scope_begin(self):
+        self._c(self.lib.sl_gemm_scope_begin(self.h))
+
+    def gemm_scope_end(self):
+        self._c(self.lib.sl_gemm_scope_end(self.h))
+
     # ---------------------------------------------------------------- R
     def _scalar(self, fn, x):
         out = self.empty(1, x.dtype)

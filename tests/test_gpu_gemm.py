@@ -104,13 +104,16 @@ def test_tile_configs(cfg, mode):
     try:
         ctx = S.Context(0)
         md = S.GEMM_3XTF32 if mode == "3xtf32" else S.GEMM_TF32
-        for (m, n, k) in [(128, 256, 128), (640, 768, 1024), (300, 700, 200), (4096, 512, 96), (1111, 2222, 333)]:
-            rng = np.random.default_rng(m + n + k)
-            a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
-            t = truth(0, 0, m, n, k, a, b)
-            got = run(ctx, 0, 0, m, n, k, a, b, md)
-            err = np.max(np.abs(got - t))
-            assert err <= (4 * k * 2.0 ** -24 if mode == "3xtf32" else 8 * np.sqrt(k) * 2.0 ** -11), (cfg, mode, m, n, k, err)
+        # NN / NT / TN: with cfg 4 (2-CTA) non-K-contiguous operands are consumed MN-major (no transposing pass) when their
+        # extent is a multiple of 4, and through a transposing split otherwise (1111 x 2222) — both paths are exercised
+        for (m, n, k) in [(128, 256, 128), (640, 768, 1024), (300, 700, 200), (4096, 512, 96), (1111, 2222, 333), (512, 1024, 40)]:
+            for (ta, tb) in ((0, 0), (0, 1), (1, 0), (1, 1)):
+                rng = np.random.default_rng(m + n + k)
+                a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
+                t = truth(ta, tb, m, n, k, a, b)
+                got = run(ctx, ta, tb, m, n, k, a, b, md)
+                err = np.max(np.abs(got - t))
+                assert err <= (4 * k * 2.0 ** -24 if mode == "3xtf32" else 8 * np.sqrt(k) * 2.0 ** -11), (cfg, mode, ta, tb, m, n, k, err)
         ctx.close()
     finally:
         os.environ.pop("SLICED_GEMM_CFG", None)
@@ -164,6 +167,45 @@ def test_gemm_grad_matches_oracle(ctx):
     dl = ctx.array(np.zeros(m * k, np.float32))
     ctx.gemm_grad(m, k, n, ctx.array(lhs), ctx.array(rhs), dl, None, ctx.array(og), False, S.GEMM_3XTF32)
     assert np.max(np.abs(dl.numpy() - lg_ref)) <= 4 * n * 2.0 ** -24 * 2
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
+def test_plane_scope_is_bit_identical_and_tracks_overwrites(mode):
+    """sl_gemm_scope_begin/_end: operand planes are reused across gemms on the same buffer; results must be bit-identical to
+    the unscoped calls, a gemm that overwrites a cached buffer must invalidate it, and the second iteration of the same call
+    sequence (slots reused, no reallocation) must agree too."""
+    import sliced_b200 as S
+    md = S.GEMM_3XTF32 if mode == "3xtf32" else S.GEMM_TF32
+    ctx = S.Context(0)
+    m = k = n = 512  # big enough for the 2-CTA kernel with MN-major operands
+    rng = np.random.default_rng(5)
+    x = ctx.array(rng.uniform(-1, 1, m * k).astype(np.float32))
+    w = ctx.array(rng.uniform(-1, 1, k * n).astype(np.float32))
+    g = ctx.array(rng.uniform(-1, 1, m * n).astype(np.float32))
+
+    def sequence():
+        y = ctx.gemm(m, k, n, x, w, mode=md)          # x: A K-major, w: B MN-major
+        dw = ctx.gemm_tn(k, n, m, x, g, mode=md)      # x: A MN-major (same flat planes), g: B MN-major
+        dx = ctx.gemm_nt(m, k, n, g, w, mode=md)      # g: A K-major, w: B K-major
+        y2 = ctx.gemm(m, n, n, y, w, mode=md)         # y was WRITTEN by a gemm above, then read
+        ctx.gemm(m, k, n, x, w, out=y, mode=md)       # overwrite y (same values), planes of y must be re-derived next
+        ctx.gemm(m, k, n, g, w, out=y, mode=md)       # now different values in y
+        y3 = ctx.gemm(m, n, n, y, w, mode=md)
+        return [t.numpy().copy() for t in (dw, dx, y2, y3)]
+
+    plain = sequence()
+    for _ in range(2):
+        ctx.gemm_scope_begin()
+        scoped = sequence()
+        ctx.gemm_scope_end()
+        for p, s in zip(plain, scoped):
+            assert np.array_equal(p, s)
+    # gemm_grad (implicit scope) == the two explicit gemms
+    dl, dr = ctx.empty(m * k, np.float32), ctx.empty(k * n, np.float32)
+    ctx.gemm_grad(m, k, n, x, w, dl, dr, g, False, md)
+    assert np.array_equal(dl.numpy(), plain[1])
+    assert np.array_equal(dr.numpy(), plain[0])
+    ctx.close()
 
 
 def test_3xtf32_is_fp32_class_on_ill_scaled_data(ctx):
