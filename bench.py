@@ -8,7 +8,7 @@ data-parallel along the batch with one NCCL sum-all-reduce of the 134 MB gradien
 One "step" = zero_grad -> 3 x (gemm, add_row_mut, relu|softmax) -> accuracy + loss -> backward_with (tape) -> all-reduce ->
 SGD, exactly the op sequence of examples/nn.rs:184-237, run through the C++ host layer over the C ABI.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling strong|weak] [--gemm-mode 3xtf32|tf32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling strong|weak] [--gemm-mode 3xtf32|tf32|3xf16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 value   whole-job samples/s with the batch already resident in HBM (device-timed with CUDA events, max over ranks)
@@ -216,7 +216,7 @@ def run_ours(args):
 
     stream = torch.cuda.current_stream()
     dev = CUDA(local_rank, cached=True, stream=stream.cuda_stream)
-    dev.set_gemm_mode(S.GEMM_TF32 if args.gemm_mode == "tf32" else S.GEMM_3XTF32)
+    dev.set_gemm_mode({"tf32": S.GEMM_TF32, "3xtf32": S.GEMM_3XTF32, "3xf16": S.GEMM_3XF16}[args.gemm_mode])
     lib = capi.load()
     ctx = dev.ctx_handle
 
@@ -336,15 +336,19 @@ def run_ours(args):
 
     if rank == 0:
         pk = peaks()
-        tf32_peak = pk["bf16_sustained"] / 2.0
+        f16 = args.gemm_mode == "3xf16"
+        # the pipe the kernel runs on: kind::f16 at the measured bf16 rate, kind::tf32 at half of it
+        tf32_peak = pk["bf16_sustained"] if f16 else pk["bf16_sustained"] / 2.0
         eff = (t_fl.value / (t_ms.value * 1e-3)) / 1e12 if t_ms.value > 0 else 0.0
         mult = 1 if args.gemm_mode == "tf32" else 3
-        roofline = dict(bound="tensor", kernel="gemm_tf32_kernel (tcgen05 kind::tf32, TMA, TMEM)", achieved=eff, peak=tf32_peak, unit="TFLOP/s",
+        roofline = dict(bound="tensor", kernel="gemm_tf32_2cta_kernel (tcgen05 cta_group::2 %s, TMA, TMEM)" % ("kind::f16" if f16 else "kind::tf32"),
+                        achieved=eff, peak=tf32_peak, unit="TFLOP/s",
                         frac=eff / tf32_peak, traffic=ncu_traffic(),
-                        peak_src=f"{pk['src']}: bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate); kernel timed inside a long step",
+                        peak_src=(f"{pk['src']}: bf16_tflops_sustained (kind::f16 runs at the bf16 rate); kernel timed inside a long step" if f16 else
+                                  f"{pk['src']}: bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate); kernel timed inside a long step"),
                         issued_tflops=eff * mult, pipe_util=eff * mult / tf32_peak,
                         note=f"achieved = algorithmic 2MNK flops of the {n_l.value} tensor-core gemm launches / their summed CUDA-event time "
-                             f"({t_ms.value / max(n_l.value, 1):.3f} ms avg); 3xTF32 issues {mult}x those flops to the tensor pipe",
+                             f"({t_ms.value / max(n_l.value, 1):.3f} ms avg); {args.gemm_mode} issues {mult}x those flops to the tensor pipe",
                         gemm_share_of_step=t_ms.value / ms_total if ms_total > 0 else None,
                         step_effective_tflops=step_flops(batch) / (ms_total / args.steps * 1e-3) / 1e12)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
@@ -372,7 +376,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
-    ap.add_argument("--gemm-mode", choices=["3xtf32", "tf32"], default="3xtf32")
+    ap.add_argument("--gemm-mode", choices=["3xtf32", "tf32", "3xf16"], default="3xf16")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="run the op-by-op tape instead of the fused-epilogue step (bit-identical results)")

@@ -87,9 +87,12 @@ typedef enum sl_unop {
 
 /* gemm arithmetic mode (f32 only; f64/i32 always use the CUDA-core kernel). */
 typedef enum sl_gemm_mode {
-    SL_GEMM_3XTF32 = 0, /* default: tcgen05 kind::tf32, 3 MMAs per k-slice (hi*hi + hi*lo + lo*hi), fp32-class accuracy */
+    SL_GEMM_3XTF32 = 0, /* tcgen05 kind::tf32, 3 MMAs per k-slice (hi*hi + hi*lo + lo*hi), fp32-class accuracy */
     SL_GEMM_TF32 = 1,   /* flagged fast mode: one tcgen05 kind::tf32 MMA per k-slice */
-    SL_GEMM_SIMT = 2    /* exact fp32 FMA accumulation on CUDA cores (any shape / dtype) */
+    SL_GEMM_SIMT = 2,   /* exact fp32 FMA accumulation on CUDA cores (any shape / dtype) */
+    SL_GEMM_3XF16 = 3   /* default: tcgen05 kind::f16 on fp16 hi/lo planes of the operands after an exact power-of-two scaling per output
+                           row / column: the same 22-bit operand split and 3 MMAs per k-slice as 3XTF32 at twice the MMA rate.
+                           Shapes the fp16 path cannot take (small, or rows not a multiple of 8) silently use 3XTF32. */
 } sl_gemm_mode;
 
 /* ---------------------------------------------------------------- context / memory */
@@ -106,7 +109,8 @@ int sl_ctx_destroy(sl_ctx* ctx);
 const char* sl_last_error_string(sl_ctx* ctx);
 void* sl_ctx_stream(sl_ctx* ctx);
 int sl_ctx_device(sl_ctx* ctx);
-/* Default gemm mode used when an entry point is passed mode < 0. Also read from env SLICED_GEMM_MODE={3xtf32,tf32,simt}. */
+/* Default gemm mode used when an entry point is passed mode < 0. Also read from env SLICED_GEMM_MODE={3xf16,3xtf32,tf32,simt}.
+ * The built-in default is SL_GEMM_3XF16. */
 int sl_ctx_set_gemm_mode(sl_ctx* ctx, int mode);
 /* Number of kernels this library launched on ctx since creation (bench.py's gpu_launches). */
 uint64_t sl_ctx_launch_count(sl_ctx* ctx);

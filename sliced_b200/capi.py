@@ -20,7 +20,7 @@ F32, F64, I32 = 0, 1, 2
 ADD, SUB, MUL, DIV = 0, 1, 2, 3
 (UN_SQUARE, UN_POW, UN_RELU, UN_TANH, UN_SIGMOID, UN_EXP, UN_LN, UN_NEG_LN, UN_CLIP, UN_NEG, UN_MUL_SCALAR,
  UN_NEG_DIV_SCALAR, UN_ADD_SCALAR) = range(13)
-GEMM_DEFAULT, GEMM_3XTF32, GEMM_TF32, GEMM_SIMT = -1, 0, 1, 2
+GEMM_DEFAULT, GEMM_3XTF32, GEMM_TF32, GEMM_SIMT, GEMM_3XF16 = -1, 0, 1, 2, 3
 
 
 class SlicedError(RuntimeError):

@@ -16,7 +16,7 @@ struct sl_ctx {
     cudaStream_t stream = nullptr;
     bool owns_stream = false;
     int num_sms = 148;
-    int gemm_mode = SL_GEMM_3XTF32;
+    int gemm_mode = SL_GEMM_3XF16;
     uint64_t launches = 0;
     std::string last_error;
     // grow-only scratch (reduction partials, gemm operand planes); owned by the ctx, never user visible

@@ -85,7 +85,8 @@ static int ctx_create_common(int device, void* stream, bool borrow, sl_ctx** out
     if (env) {
         if (!strcmp(env, "tf32")) ctx->gemm_mode = SL_GEMM_TF32;
         else if (!strcmp(env, "simt")) ctx->gemm_mode = SL_GEMM_SIMT;
-        else ctx->gemm_mode = SL_GEMM_3XTF32;
+        else if (!strcmp(env, "3xf16")) ctx->gemm_mode = SL_GEMM_3XF16;
+        else if (!strcmp(env, "3xtf32")) ctx->gemm_mode = SL_GEMM_3XTF32;
     }
     *out_ctx = ctx;
     return SL_OK;
@@ -127,7 +128,7 @@ uint64_t sl_ctx_launch_count(sl_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int sl_ctx_set_gemm_mode(sl_ctx* ctx, int mode) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
-    SL_REQUIRE(ctx, mode >= SL_GEMM_3XTF32 && mode <= SL_GEMM_SIMT, "bad mode");
+    SL_REQUIRE(ctx, mode >= SL_GEMM_3XTF32 && mode <= SL_GEMM_3XF16, "bad mode");
     ctx->gemm_mode = mode;
     return SL_OK;
 }

@@ -23,6 +23,8 @@
 //   barriers    full[STAGES], empty[STAGES] (TMA <-> MMA), tmem_full[2], tmem_empty[2] (MMA <-> epilogue)
 #include <cuda.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 int sl_gemm_simt(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
@@ -159,11 +161,28 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
     d |= (uint64_t)1 << 61;                        // SWIZZLE_128B_BASE32B
     return d;
 }
+// 16-bit MN-major operand tile [64 k x 128 mn] fp16: two 64-mn chunks, each one TMA box {64 mn, 64 k} = 64 rows of 128 bytes with
+// the standard 128-byte swizzle (UMMA layout type 2).  Canonical form ((T,8,m),(8,k)) : ((1,T,LBO),(8T,SBO)), T = 8 halves per
+// 16 B: LBO = distance between 64-mn chunks (8192 B), SBO = distance between groups of 8 k-rows (1024 B).  One MMA (K = 16)
+// consumes two such groups (2048 B) of every chunk.
+__device__ __forceinline__ uint64_t make_smem_desc_mn16(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(8192 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor: D = F32 (bits[4,6)=1), A = B = TF32 (bits[7,10)=2, [10,13)=2), A / B major (bit 15 / 16: 0 = K-major,
 // 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
+}
+// same with A = B = F16 (format code 0), for kind::f16
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------ the MMA kernel
@@ -194,10 +213,16 @@ struct GemmParams {
     int splits;             // split-K factor (2-CTA kernel): partial s is written to C + s*M*N, folded afterwards by the host
     float* C2;              // optional second output: C2 = (v >= 0) * v of the value stored to C (fused Matrix::relu)
     const float* mask_src;  // optional [M x N]: v *= (mask_src >= 0) before the store (fused relu gradient)
+    const float* row_scale; // 3xFP16 mode: acc is multiplied by row_scale[row] * col_scale[col] (exact powers of two undoing the
+    const float* col_scale; //   operand scaling) before anything else; both NULL otherwise
 };
 
 // shared epilogue arithmetic of both MMA kernels: 4 consecutive columns of one output row
-__device__ __forceinline__ void epilogue_store4(const GemmParams& p, float* crow, size_t row_off, int n0, float4 v) {
+__device__ __forceinline__ void epilogue_store4(const GemmParams& p, float* crow, size_t row_off, int n0, float4 v, float rs = 1.f) {
+    if (p.col_scale) {
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0));
+        v.x = (v.x * rs) * cs.x; v.y = (v.y * rs) * cs.y; v.z = (v.z * rs) * cs.z; v.w = (v.w * rs) * cs.w;
+    }
     if (p.accumulate) {
         const float4 o = *reinterpret_cast<const float4*>(crow + n0);
         v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -223,7 +248,8 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, float* crow
         *reinterpret_cast<float4*>(p.C2 + row_off + n0) = r;
     }
 }
-__device__ __forceinline__ void epilogue_store1(const GemmParams& p, float* crow, size_t row_off, int n, float v) {
+__device__ __forceinline__ void epilogue_store1(const GemmParams& p, float* crow, size_t row_off, int n, float v, float rs = 1.f) {
+    if (p.col_scale) v = (v * rs) * __ldg(p.col_scale + n);
     if (p.accumulate) v += crow[n];
     if (p.bias) v += __ldg(p.bias + n);
     if (p.mask_src) v = (__ldg(p.mask_src + row_off + n) >= 0.f ? 1.f : 0.f) * v;
@@ -501,18 +527,35 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
         : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == 1) umma_f16_2sm(tmem_d, desc_a, desc_b, idesc, accumulate);
+    else umma_tf32_2sm(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
 // arrive (once the issued MMAs retire) on the barrier at the same shared-memory offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                  : "memory");
 }
 
-template <int TERMS, int STAGES>
+// KIND 0: tf32 planes (4-byte elements, 32 k per 128-byte row, MMA K = 8); KIND 1: fp16 planes (64 k per row, MMA K = 16)
+template <int TERMS, int STAGES, int KIND = 0>
 struct Gemm2Cfg {
-    static constexpr int BLOCK_K = 32;
+    static constexpr int ELEM = KIND == 1 ? 2 : 4;
+    static constexpr int BLOCK_K = 128 / ELEM;
+    static constexpr int MMA_K = 32 / ELEM;
     static constexpr int TILE_M = 256, TILE_N = 256;       // per CTA pair
-    static constexpr int A_BYTES = 128 * BLOCK_K * 4;      // this CTA's 128 rows of A
-    static constexpr int B_BYTES = 128 * BLOCK_K * 4;      // this CTA's 128 rows (N) of B
+    static constexpr int A_BYTES = 128 * 128;              // this CTA's 128 rows of A, 128 bytes of k each
+    static constexpr int B_BYTES = 128 * 128;              // this CTA's 128 rows (N) of B
     static constexpr int PLANES = TERMS == 3 ? 2 : 1;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
     static constexpr int TMEM_COLS = 2 * TILE_N;           // two chunk buffers of 256 fp32 columns
@@ -521,11 +564,11 @@ struct Gemm2Cfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "stage ring does not fit in shared memory");
 };
 
-template <int TERMS, int STAGES, bool A_MN, bool B_MN>
+template <int TERMS, int STAGES, bool A_MN, bool B_MN, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
-    using Cfg = Gemm2Cfg<TERMS, STAGES>;
+    using Cfg = Gemm2Cfg<TERMS, STAGES, KIND>;
     constexpr int BLOCK_K = Cfg::BLOCK_K;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -540,6 +583,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
+    // MN-major chunking: tf32 -> four 32-mn chunks of BLOCK_K rows x 128 B; fp16 -> two 64-mn chunks
+    constexpr int MN_CHUNKS = KIND == 1 ? 2 : 4;
+    constexpr int MN_CHUNK_ROWS = 128 / MN_CHUNKS;
+    constexpr int MN_CHUNK_BYTES = BLOCK_K * 128;
+    constexpr int MN_KSTEP_BYTES = Cfg::MMA_K * 128;
     const bool leader = rank == 0;
 
     if (warp == 0 && lane == 0) {
@@ -617,13 +665,13 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                     const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
                     const uint32_t fb = mapa_shared(full_bar(stage), 0);  // the leader's barrier, as a shared::cluster address
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-                    // K-major plane: one box {BLOCK_K k, 128 rows}; MN-major plane: four boxes {32 mn, BLOCK_K k}, one per 32-mn chunk
+                    // K-major plane: one box {BLOCK_K k, 128 rows}; MN-major plane: one box {32 | 64 mn, BLOCK_K k} per chunk
                     auto load_plane = [&](uint32_t dst, const CUtensorMap* map, int row0, bool mn) {
                         if (!mn) {
                             tma_load_2d_2sm(dst, map, fb, kb * BLOCK_K, row0);
                         } else {
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) tma_load_2d_2sm(dst + g * (BLOCK_K * 128), map, fb, row0 + g * 32, kb * BLOCK_K);
+                            for (int g = 0; g < MN_CHUNKS; ++g) tma_load_2d_2sm(dst + g * MN_CHUNK_BYTES, map, fb, row0 + g * MN_CHUNK_ROWS, kb * BLOCK_K);
                         }
                     };
                     load_plane(sa, &map_a_hi, row_a, A_MN);
@@ -643,7 +691,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     } else if (warp == 1) {
         // ================================================================= MMA issuer (leader CTA only)
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(Cfg::TILE_M, Cfg::TILE_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            constexpr uint32_t idesc = KIND == 1 ? make_idesc_f16(Cfg::TILE_M, Cfg::TILE_N, A_MN ? 1 : 0, B_MN ? 1 : 0)
+                                                 : make_idesc_tf32(Cfg::TILE_M, Cfg::TILE_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            // K-major descriptors are byte-based (128-byte rows, 8-row groups) and identical for both element sizes
+            auto desc_k = [](uint32_t addr) { return make_smem_desc<32>(addr); };
+            auto desc_mn = [](uint32_t addr) { return KIND == 1 ? make_smem_desc_mn16(addr) : make_smem_desc_mn<32>(addr); };
             int stage = 0;
             uint32_t phase = 0;
             uint32_t g = 0;
@@ -662,22 +714,22 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                         tc_fence_after();
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                         const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
-                        const uint64_t da_hi = A_MN ? make_smem_desc_mn<BLOCK_K>(sa) : make_smem_desc<BLOCK_K>(sa);
-                        const uint64_t db_hi = B_MN ? make_smem_desc_mn<BLOCK_K>(sb) : make_smem_desc<BLOCK_K>(sb);
-                        const uint64_t da_lo = A_MN ? make_smem_desc_mn<BLOCK_K>(sa + Cfg::A_BYTES) : make_smem_desc<BLOCK_K>(sa + Cfg::A_BYTES);
-                        const uint64_t db_lo = B_MN ? make_smem_desc_mn<BLOCK_K>(sb + Cfg::B_BYTES) : make_smem_desc<BLOCK_K>(sb + Cfg::B_BYTES);
+                        const uint64_t da_hi = A_MN ? desc_mn(sa) : desc_k(sa);
+                        const uint64_t db_hi = B_MN ? desc_mn(sb) : desc_k(sb);
+                        const uint64_t da_lo = A_MN ? desc_mn(sa + Cfg::A_BYTES) : desc_k(sa + Cfg::A_BYTES);
+                        const uint64_t db_lo = B_MN ? desc_mn(sb + Cfg::B_BYTES) : desc_k(sb + Cfg::B_BYTES);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            // one k-slice (8 k): K-major -> 32 bytes further along the 128-byte row; MN-major -> the next 8-row group (1024 B)
-                            const uint64_t koff_a = (uint64_t)((A_MN ? k * 1024 : k * UMMA_K * 4) >> 4);
-                            const uint64_t koff_b = (uint64_t)((B_MN ? k * 1024 : k * UMMA_K * 4) >> 4);
+                        for (int k = 0; k < 4; ++k) {
+                            // one k-slice (32 bytes of k): K-major -> 32 bytes further along the 128-byte row; MN-major -> MMA_K rows further
+                            const uint64_t koff_a = (uint64_t)((A_MN ? k * MN_KSTEP_BYTES : k * 32) >> 4);
+                            const uint64_t koff_b = (uint64_t)((B_MN ? k * MN_KSTEP_BYTES : k * 32) >> 4);
                             const uint32_t first = (kb == kb_begin && k == 0) ? 0u : 1u;
                             if (TERMS == 3) {
-                                umma_tf32_2sm(tmem_d, da_lo + koff_a, db_hi + koff_b, idesc, first);
-                                umma_tf32_2sm(tmem_d, da_hi + koff_a, db_lo + koff_b, idesc, 1u);
-                                umma_tf32_2sm(tmem_d, da_hi + koff_a, db_hi + koff_b, idesc, 1u);
+                                umma_2sm<KIND>(tmem_d, da_lo + koff_a, db_hi + koff_b, idesc, first);
+                                umma_2sm<KIND>(tmem_d, da_hi + koff_a, db_lo + koff_b, idesc, 1u);
+                                umma_2sm<KIND>(tmem_d, da_hi + koff_a, db_hi + koff_b, idesc, 1u);
                             } else {
-                                umma_tf32_2sm(tmem_d, da_hi + koff_a, db_hi + koff_b, idesc, first);
+                                umma_2sm<KIND>(tmem_d, da_hi + koff_a, db_hi + koff_b, idesc, first);
                             }
                         }
                         umma_commit_2sm(empty_bar(stage), 0x3);   // frees the stage in BOTH CTAs
@@ -731,16 +783,17 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             if (row < p.M) {
                 float* crow = p.C + (size_t)split * p.M * p.N + (size_t)row * p.N;
                 const int nbase = n_blk * Cfg::TILE_N + col0;
+                const float rs = p.row_scale ? __ldg(p.row_scale + row) : 1.f;
 #pragma unroll
                 for (int j = 0; j < CPW; j += 4) {
                     const int n0 = nbase + j;
                     if (n0 >= p.N) break;
                     if (p.c_vec_ok && n0 + 4 <= p.N) {
-                        epilogue_store4(p, crow, (size_t)row * p.N, n0, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+                        epilogue_store4(p, crow, (size_t)row * p.N, n0, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), rs);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (n0 + e < p.N) epilogue_store1(p, crow, (size_t)row * p.N, n0 + e, acc[j + e]);
+                            if (n0 + e < p.N) epilogue_store1(p, crow, (size_t)row * p.N, n0 + e, acc[j + e], rs);
                     }
                 }
             }
@@ -835,6 +888,128 @@ __global__ void __launch_bounds__(256) prep_transpose_kernel(size_t K, size_t R,
     }
 }
 
+// ---- 3xFP16 operand prep.  x is first multiplied by an exact power of two chosen per OUTPUT index (per row of A, per column
+// of B) so that the largest magnitude along the contraction lands in [2^14, 2^15); then hi = fp16(x'), lo = fp16(x' - hi).  fp16
+// and tf32 carry the same 11 significant bits, so hi + lo represents x' to 22 bits exactly like the tf32 split; the scaling only
+// exists to fit fp16's 5-bit exponent (elements below 2^-16 of their row's maximum start to lose low bits: absolute floor
+// 2^-40 of the row maximum).  The epilogue multiplies by the inverse scales, again exact.
+__device__ __forceinline__ float scale_for_max(float m, float* inv) {
+    if (!(m > 0.f) || !isfinite(m)) { *inv = 1.f; return 1.f; }
+    int e;
+    frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)  ->  m * 2^(15 - e) in [2^14, 2^15)
+    e = 15 - e;
+    e = e < -126 ? -126 : (e > 126 ? 126 : e);
+    *inv = ldexpf(1.f, -e);
+    return ldexpf(1.f, e);
+}
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    const float h = __half2float(hi);
+    lo = isfinite(h) ? __float2half_rn(x - h) : __float2half_rn(0.f);
+}
+__device__ __forceinline__ float absmax4(float m, const float4& v) {
+    return fmaxf(fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
+}
+__device__ __forceinline__ void split4_store(const float4& v, float sx, float sy, float sz, float sw, __half* hi, __half* lo) {
+    __half h[4], l[4];
+    split_f16(v.x * sx, h[0], l[0]); split_f16(v.y * sy, h[1], l[1]);
+    split_f16(v.z * sz, h[2], l[2]); split_f16(v.w * sw, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<const uint2*>(l);
+}
+
+// K-contiguous operand [R x K] (K % 4 == 0): one block per row.  Rows of up to 8192 elements are held in registers between the
+// max pass and the split pass (one HBM read); longer rows are re-read (L2).
+__global__ void __launch_bounds__(256) prep16_rows_kernel(size_t R, size_t K, const float* __restrict__ src, __half* __restrict__ hi,
+                                                          __half* __restrict__ lo, float* __restrict__ scale_inv) {
+    __shared__ float red[8];
+    __shared__ float bcast;
+    const size_t nv = K / 4;
+    const bool cached = nv <= 8 * 256;
+    for (size_t row = blockIdx.x; row < R; row += gridDim.x) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + row * K);
+        float4 v[8];
+        float m = 0.f;
+        if (cached) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const size_t idx = threadIdx.x + (size_t)i * 256;
+                if (idx < nv) {
+                    v[i] = __ldg(s4 + idx);
+                    m = absmax4(m, v[i]);
+                }
+            }
+        } else {
+            for (size_t idx = threadIdx.x; idx < nv; idx += 256) m = absmax4(m, __ldg(s4 + idx));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = red[0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w]);
+            float inv;
+            bcast = scale_for_max(t, &inv);
+            scale_inv[row] = inv;
+        }
+        __syncthreads();
+        const float sc = bcast;
+        __half* h = hi + row * K;
+        __half* l = lo + row * K;
+        if (cached) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const size_t idx = threadIdx.x + (size_t)i * 256;
+                if (idx < nv) split4_store(v[i], sc, sc, sc, sc, h + idx * 4, l + idx * 4);
+            }
+        } else {
+            for (size_t idx = threadIdx.x; idx < nv; idx += 256) split4_store(__ldg(s4 + idx), sc, sc, sc, sc, h + idx * 4, l + idx * 4);
+        }
+        __syncthreads();
+    }
+}
+
+// MN-contiguous operand [K x R] (R % 4 == 0), scale per column r over all K rows.
+// pass 1: grid (column blocks of 1024, slabs of rows) -> partial[slab][R] = max |x| over the slab
+__global__ void __launch_bounds__(256) prep16_colmax_kernel(size_t K, size_t R, size_t rows_per_slab, const float* __restrict__ src,
+                                                            float* __restrict__ partial) {
+    const size_t c = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (c >= R) return;
+    const size_t k0 = (size_t)blockIdx.y * rows_per_slab;
+    const size_t k1 = k0 + rows_per_slab < K ? k0 + rows_per_slab : K;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t k = k0; k < k1; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + k * R + c));
+        m.x = fmaxf(m.x, fabsf(v.x)); m.y = fmaxf(m.y, fabsf(v.y)); m.z = fmaxf(m.z, fabsf(v.z)); m.w = fmaxf(m.w, fabsf(v.w));
+    }
+    *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * R + c) = m;
+}
+// pass 2: fold the slabs -> scale[r], scale_inv[r]
+__global__ void __launch_bounds__(256) prep16_colscale_kernel(size_t R, int slabs, const float* __restrict__ partial, float* __restrict__ scale,
+                                                              float* __restrict__ scale_inv) {
+    const size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= R) return;
+    float m = 0.f;
+    for (int s = 0; s < slabs; ++s) m = fmaxf(m, partial[(size_t)s * R + r]);
+    float inv;
+    scale[r] = scale_for_max(m, &inv);
+    scale_inv[r] = inv;
+}
+// pass 3: element-wise split with the column's scale (planes keep the [K x R] layout)
+__global__ void __launch_bounds__(256) prep16_cols_kernel(size_t K, size_t R, const float* __restrict__ src, const float* __restrict__ scale,
+                                                          __half* __restrict__ hi, __half* __restrict__ lo) {
+    const size_t rv = R / 4;
+    const size_t total = K * rv;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = (i % rv) * 4;
+        const Pack<float> x = ld_stream(src + i * 4);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+        split4_store(make_float4(x.v[0], x.v[1], x.v[2], x.v[3]), sc.x, sc.y, sc.z, sc.w, hi + i * 4, lo + i * 4);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -852,15 +1027,15 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // K-major operand plane [rows x K] with leading dimension ld (floats); box = BLOCK_K x box_rows
-static int make_map(sl_ctx* ctx, CUtensorMap* map, const float* base, size_t rows, size_t K, size_t ld, int block_k, int box_rows) {
+static int make_map(sl_ctx* ctx, CUtensorMap* map, const void* base, size_t rows, size_t K, size_t ld, int block_k, int box_rows, int elem = 4) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return sl_set_error(ctx, SL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * elem};
     cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUtensorMapSwizzle sw = block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+    CUtensorMapSwizzle sw = block_k * elem == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = enc(map, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sl_set_error(ctx, SL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%zu K=%zu ld=%zu", (int)r, rows, K, ld);
     return SL_OK;
@@ -904,27 +1079,30 @@ static int launch_cfg(sl_ctx* ctx, const GemmParams& p, const float* a_hi, const
 
 // 2-CTA (cta_group::2) launch: clusters of 2 CTAs, one 256x256 tile per cluster; each CTA's TMA box is 128 rows of A / of B
 // MN-major plane: stored [K x rows] with leading dimension ld (rows contiguous); box = 32 rows(mn) x BLOCK_K k
-static int make_map_mn(sl_ctx* ctx, CUtensorMap* map, const float* base, size_t rows, size_t K, size_t ld, int block_k) {
+//                 (fp16: box = 64 rows(mn) x BLOCK_K k, standard 128-byte swizzle)
+static int make_map_mn(sl_ctx* ctx, CUtensorMap* map, const void* base, size_t rows, size_t K, size_t ld, int block_k, int elem = 4) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return sl_set_error(ctx, SL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)K};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32u, (cuuint32_t)block_k};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * elem};
+    cuuint32_t box[2] = {elem == 2 ? 64u : 32u, (cuuint32_t)block_k};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, elem == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sl_set_error(ctx, SL_ERR_CUDA, "cuTensorMapEncodeTiled (MN-major) failed (%d) rows=%zu K=%zu ld=%zu", (int)r, rows, K, ld);
     return SL_OK;
 }
 
-template <int TERMS, int STAGES, bool A_MN, bool B_MN>
-static int launch_cfg_2cta(sl_ctx* ctx, const GemmParams& p, const float* a_hi, const float* a_lo, size_t lda, const float* b_hi,
-                           const float* b_lo, size_t ldb) {
-    using Cfg = Gemm2Cfg<TERMS, STAGES>;
+template <int TERMS, int STAGES, bool A_MN, bool B_MN, int KIND = 0>
+static int launch_cfg_2cta(sl_ctx* ctx, const GemmParams& p, const void* a_hi, const void* a_lo, size_t lda, const void* b_hi,
+                           const void* b_lo, size_t ldb) {
+    using Cfg = Gemm2Cfg<TERMS, STAGES, KIND>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    auto mk = [&](CUtensorMap* m, const float* base, size_t rows, size_t ld, bool mn) {
-        return mn ? make_map_mn(ctx, m, base, rows, p.K, ld, Cfg::BLOCK_K) : make_map(ctx, m, base, rows, p.K, ld, Cfg::BLOCK_K, 128);
+    auto mk = [&](CUtensorMap* m, const void* base, size_t rows, size_t ld, bool mn) {
+        return mn ? make_map_mn(ctx, m, base, rows, p.K, ld, Cfg::BLOCK_K, Cfg::ELEM)
+                  : make_map(ctx, m, base, rows, p.K, ld, Cfg::BLOCK_K, 128, Cfg::ELEM);
     };
     if ((rc = mk(&ma_hi, a_hi, p.M, lda, A_MN)) != SL_OK) return rc;
     if ((rc = mk(&mb_hi, b_hi, p.N, ldb, B_MN)) != SL_OK) return rc;
@@ -934,7 +1112,7 @@ static int launch_cfg_2cta(sl_ctx* ctx, const GemmParams& p, const float* a_hi, 
         if ((rc = mk(&ma_lo, a_lo, p.M, lda, A_MN)) != SL_OK) return rc;
         if ((rc = mk(&mb_lo, b_lo, p.N, ldb, B_MN)) != SL_OK) return rc;
     }
-    auto kern = gemm_tf32_2cta_kernel<TERMS, STAGES, A_MN, B_MN>;
+    auto kern = gemm_tf32_2cta_kernel<TERMS, STAGES, A_MN, B_MN, KIND>;
     SL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int num_tiles = ((p.M + Cfg::TILE_M - 1) / Cfg::TILE_M) * ((p.N + Cfg::TILE_N - 1) / Cfg::TILE_N);
     const int max_clusters = ctx->num_sms / 2;
@@ -991,18 +1169,23 @@ __global__ void __launch_bounds__(256) splitk_fold_kernel(size_t total, size_t n
 
 // Runs the tensor-core kernel on prepared K-major planes: C[M x N] (=|+=) A[M x K] * B[N x K]^T (+ bias, relu).
 // a_lo / b_lo are NULL in TF32 mode.  lda / ldb in floats, multiples of 4, planes 16-byte aligned.
-int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const float* a_lo, size_t lda, const float* b_hi, const float* b_lo,
-                      size_t ldb, float* C, const float* bias, int accumulate, int relu, float* c2, const float* mask_src, int a_mn, int b_mn) {
+// kind 1: the planes are fp16 (3xFP16 mode, 2-CTA kernel only; lda / ldb in halves, multiples of 8) and row_scale [M] / col_scale [N]
+// hold the inverse operand scales applied by the epilogue.
+int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const void* a_lo, size_t lda, const void* b_hi, const void* b_lo,
+                      size_t ldb, float* C, const float* bias, int accumulate, int relu, float* c2, const float* mask_src, int a_mn, int b_mn,
+                      int kind = 0, const float* row_scale = nullptr, const float* col_scale = nullptr) {
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu; p.C2 = c2; p.mask_src = mask_src;
-    p.c_vec_ok = (N % 4 == 0) && sl_aligned16(C) && (!bias || sl_aligned16(bias)) && (!c2 || sl_aligned16(c2)) && (!mask_src || sl_aligned16(mask_src));
+    p.row_scale = row_scale; p.col_scale = col_scale;
+    p.c_vec_ok = (N % 4 == 0) && sl_aligned16(C) && (!bias || sl_aligned16(bias)) && (!c2 || sl_aligned16(c2)) && (!mask_src || sl_aligned16(mask_src)) &&
+                 (!col_scale || sl_aligned16(col_scale));
     const bool three = a_lo != nullptr;
     // K-chunk (in k-blocks of 32) accumulated inside TMEM before promotion to fp32 registers; 0 = whole K (TF32 fast mode)
     p.kc_blocks = three ? env_int("SLICED_GEMM_KC", 4) : env_int("SLICED_GEMM_KC_TF32", 0);
     // tile configuration: SLICED_GEMM_CFG = 0 auto | 1: 128x256x32 | 2: 128x256x16 (swizzle 64B, deeper ring) | 3: 128x128x32
     //                                       | 4: 2-CTA pairs (cta_group::2), 256x256x32 per pair
     const int cfg = sl_gemm_pick_cfg(ctx, M, N);
-    if (cfg != 4 && (a_mn || b_mn)) return sl_set_error(ctx, SL_ERR_INVALID_ARG, "MN-major planes need the 2-CTA kernel");
+    if (cfg != 4 && (a_mn || b_mn || kind)) return sl_set_error(ctx, SL_ERR_INVALID_ARG, "MN-major / fp16 planes need the 2-CTA kernel");
     p.splits = 1;
     // Tile raster.  Measured on the MLP shapes (tools/raster_sweep.py): narrow groups win — with 2 blocks of the LONG dimension per
     // group the tiles running concurrently span the whole short dimension, so the smaller operand (the weights: 134 MB of hi/lo
@@ -1018,12 +1201,13 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const
         const long pairs = ctx->num_sms / 2;
         auto eff = [&](long units) { return (double)units / (double)(((units + pairs - 1) / pairs) * pairs); };
         int best = 1;
-        const int num_kb = (K + 31) / 32;
+        const int block_k = kind == 1 ? 64 : 32;
+        const int num_kb = (K + block_k - 1) / block_k;
         const int max_splits = env_int("SLICED_GEMM_MAX_SPLITS", 4);
         if (eff(tiles) < 0.92)
             for (int sp = 2; sp <= max_splits; ++sp) {
                 const int kbs = (num_kb + sp - 1) / sp;
-                if (kbs < 64 || (long)(sp - 1) * kbs >= num_kb) continue;   // keep every split >= 2048 deep and non-empty
+                if (kbs * block_k < 2048 || (long)(sp - 1) * kbs >= num_kb) continue;   // keep every split >= 2048 deep and non-empty
                 if (eff(tiles * sp) > eff(tiles * best) + 0.03) best = sp;
             }
         GemmParams q = p;
@@ -1038,8 +1222,9 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const
             q.c_vec_ok = (N % 4 == 0);
         }
         int rc;
-#define SL_2CTA(AM, BM) (three ? launch_cfg_2cta<3, 3, AM, BM>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb) \
-                               : launch_cfg_2cta<1, 6, AM, BM>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb))
+#define SL_2CTA(AM, BM) (kind == 1 ? launch_cfg_2cta<3, 3, AM, BM, 1>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb) \
+                         : three   ? launch_cfg_2cta<3, 3, AM, BM>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb)     \
+                                   : launch_cfg_2cta<1, 6, AM, BM>(ctx, q, a_hi, a_lo, lda, b_hi, b_lo, ldb))
         if (a_mn && b_mn) rc = SL_2CTA(true, true);
         else if (a_mn) rc = SL_2CTA(true, false);
         else if (b_mn) rc = SL_2CTA(false, true);
@@ -1053,14 +1238,15 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const float* a_hi, const
                   p.bias, p.relu, p.C2, p.mask_src);
         return SL_OK;
     }
+    const float *fa_hi = (const float*)a_hi, *fa_lo = (const float*)a_lo, *fb_hi = (const float*)b_hi, *fb_lo = (const float*)b_lo;
     if (three) {
-        if (cfg == 1) return launch_cfg<256, 32, 3, 2>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
-        if (cfg == 2) return launch_cfg<256, 16, 3, 4>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
-        return launch_cfg<128, 32, 3, 3>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        if (cfg == 1) return launch_cfg<256, 32, 3, 2>(ctx, p, fa_hi, fa_lo, lda, fb_hi, fb_lo, ldb);
+        if (cfg == 2) return launch_cfg<256, 16, 3, 4>(ctx, p, fa_hi, fa_lo, lda, fb_hi, fb_lo, ldb);
+        return launch_cfg<128, 32, 3, 3>(ctx, p, fa_hi, fa_lo, lda, fb_hi, fb_lo, ldb);
     } else {
-        if (cfg == 1) return launch_cfg<256, 32, 1, 4>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
-        if (cfg == 2) return launch_cfg<256, 16, 1, 8>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
-        return launch_cfg<128, 32, 1, 6>(ctx, p, a_hi, a_lo, lda, b_hi, b_lo, ldb);
+        if (cfg == 1) return launch_cfg<256, 32, 1, 4>(ctx, p, fa_hi, fa_lo, lda, fb_hi, fb_lo, ldb);
+        if (cfg == 2) return launch_cfg<256, 16, 1, 8>(ctx, p, fa_hi, fa_lo, lda, fb_hi, fb_lo, ldb);
+        return launch_cfg<128, 32, 1, 6>(ctx, p, fa_hi, fa_lo, lda, fb_hi, fb_lo, ldb);
     }
 }
 
@@ -1138,6 +1324,56 @@ __global__ void __launch_bounds__(256) epilogue_pass_kernel(size_t total, size_t
     }
 }
 
+// 3xFP16 path: scale + split both operands into fp16 hi / lo planes IN THEIR OWN LAYOUT (K-major or MN-major, never transposed)
+// and run the kind::f16 2-CTA kernel; the epilogue undoes the scaling.
+static int prep16_operand(sl_ctx* ctx, const float* src, size_t mn, size_t k, bool k_contiguous, __half* hi, __half* lo, float* scale,
+                          float* scale_inv) {
+    const size_t cap = (size_t)ctx->num_sms * 8;
+    if (k_contiguous) {  // [mn x k]
+        SL_LAUNCH(ctx, prep16_rows_kernel, (unsigned)(mn < cap * 4 ? mn : cap * 4), 256, 0, mn, k, src, hi, lo, scale_inv);
+        return SL_OK;
+    }
+    // [k x mn]: column maxima in two deterministic passes, then the element-wise split
+    const size_t col_blocks = (mn / 4 + 255) / 256;
+    size_t slabs = cap / col_blocks;
+    if (slabs < 1) slabs = 1;
+    if (slabs > (k + 31) / 32) slabs = (k + 31) / 32;   // at least 32 rows per slab
+    if (slabs > 65535) slabs = 65535;
+    const size_t rows_per_slab = (k + slabs - 1) / slabs;
+    slabs = (k + rows_per_slab - 1) / rows_per_slab;
+    void* partial = nullptr;
+    int rc = sl_ws_reserve(ctx, slabs * mn * sizeof(float), &partial);
+    if (rc != SL_OK) return rc;
+    SL_LAUNCH(ctx, prep16_colmax_kernel, dim3((unsigned)col_blocks, (unsigned)slabs, 1), 256, 0, k, mn, rows_per_slab, src, (float*)partial);
+    SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((mn + 255) / 256), 256, 0, mn, (int)slabs, (const float*)partial, scale, scale_inv);
+    const size_t total = k * (mn / 4);
+    size_t blocks = (total + 255) / 256;
+    SL_LAUNCH(ctx, prep16_cols_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, k, mn, src, (const float*)scale, hi, lo);
+    return SL_OK;
+}
+
+static int gemm_f16x3(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const float* a, const float* b, float* c, int accumulate,
+                      const Epi& epi) {
+    const bool a_kc = !trans_a, b_kc = trans_b != 0;
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t a_plane = up(m * k * 2), b_plane = up(n * k * 2), sm = up(m * 4), sn = up(n * 4);
+    char* ws = nullptr;
+    int rc = sl_ws2_reserve(ctx, 2 * a_plane + 2 * b_plane + 2 * sm + 2 * sn, (void**)&ws);
+    if (rc != SL_OK) return rc;
+    __half* a_hi = (__half*)ws;
+    __half* a_lo = (__half*)(ws + a_plane);
+    __half* b_hi = (__half*)(ws + 2 * a_plane);
+    __half* b_lo = (__half*)(ws + 2 * a_plane + b_plane);
+    float* a_sc = (float*)(ws + 2 * a_plane + 2 * b_plane);
+    float* a_inv = (float*)((char*)a_sc + sm);
+    float* b_sc = (float*)((char*)a_inv + sm);
+    float* b_inv = (float*)((char*)b_sc + sn);
+    if ((rc = prep16_operand(ctx, a, m, k, a_kc, a_hi, a_lo, a_sc, a_inv)) != SL_OK) return rc;
+    if ((rc = prep16_operand(ctx, b, n, k, b_kc, b_hi, b_lo, b_sc, b_inv)) != SL_OK) return rc;
+    return sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, a_kc ? k : m, b_hi, b_lo, b_kc ? k : n, c, epi.bias, accumulate, epi.relu, epi.c2,
+                             epi.mask_src, a_kc ? 0 : 1, b_kc ? 0 : 1, 1, a_inv, b_inv);
+}
+
 static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
                         int accumulate, int mode, const Epi& epi) {
     const float* bias = epi.bias;
@@ -1164,6 +1400,16 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
         size_t blocks = (total + 255) / 256;
         SL_LAUNCH(ctx, epilogue_pass_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, total, n, (float*)c, bias, relu, epi.c2, epi.mask_src);
         return SL_OK;
+    }
+    // 3xFP16: needs the 2-CTA kernel and 16-byte aligned fp16 rows in whatever layout the operand already has; anything else
+    // takes the 3xTF32 path below (same accuracy class, half the tensor-pipe rate).
+    if (mode == SL_GEMM_3XF16) {
+        const bool ok = sl_gemm_pick_cfg(ctx, m, n) == 4 && ((trans_a ? m : k) % 8 == 0) && ((trans_b ? k : n) % 8 == 0) && sl_aligned16(a) &&
+                        sl_aligned16(b);
+        if (ok) return gemm_f16x3(ctx, trans_a, trans_b, m, n, k, (const float*)a, (const float*)b, (float*)c, accumulate, epi);
+        if (env_int("SLICED_GEMM_F16_STRICT", 0))   // tests: make the silent 3xTF32 substitution visible
+            return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "3xFP16 path cannot take %zux%zux%zu (trans %d,%d)", m, n, k, trans_a, trans_b);
+        mode = SL_GEMM_3XTF32;
     }
     const bool three = mode == SL_GEMM_3XTF32;
     // Operand forms.  K-major = contraction index contiguous (A: !trans_a, B: trans_b).  The 2-CTA kernel also consumes MN-major

@@ -75,18 +75,18 @@ TC_SHAPES = [
 
 @pytest.mark.parametrize("shape", TC_SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("trans", [(0, 0), (0, 1), (1, 0)], ids=["NN", "NT", "TN"])
-@pytest.mark.parametrize("mode", ["3xtf32", "tf32"])
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32", "3xf16"])
 def test_tensor_core_gemm(ctx, shape, trans, mode):
     import sliced_b200 as S
     m, n, k = shape
     ta, tb = trans
-    md = S.GEMM_3XTF32 if mode == "3xtf32" else S.GEMM_TF32
+    md = {"3xtf32": S.GEMM_3XTF32, "tf32": S.GEMM_TF32, "3xf16": S.GEMM_3XF16}[mode]
     rng = np.random.default_rng(42 + m + n + k)
     a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
     t = truth(ta, tb, m, n, k, a, b)
     got = run(ctx, ta, tb, m, n, k, a, b, md)
     err = np.max(np.abs(got - t))
-    if mode == "3xtf32":
+    if mode != "tf32":   # 3xf16 on shapes its kernel cannot take is 3xtf32; either way the fp32-class bound holds
         ref = O.gemm_ex(ta, tb, m, n, k, a, b)
         ref_err = np.max(np.abs(ref - t))
         assert err <= 4 * k * 2.0 ** -24, f"3xTF32 err {err} (oracle sgemm err {ref_err})"
@@ -117,6 +117,89 @@ def test_tile_configs(cfg, mode):
         ctx.close()
     finally:
         os.environ.pop("SLICED_GEMM_CFG", None)
+
+
+F16_SHAPES = [(128, 256, 128), (256, 256, 64), (640, 768, 1024), (304, 704, 200), (4096, 512, 96), (1112, 2224, 336), (512, 1024, 40),
+              (264, 8, 72), (8, 264, 4104), (2048, 2048, 2048)]
+
+
+@pytest.mark.parametrize("shape", F16_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_3xf16_kernel(shape, monkeypatch):
+    """SL_GEMM_3XF16 through the kind::f16 2-CTA kernel itself (STRICT: no silent 3xTF32 substitution), all four operand
+    layouts (K-major row-scaled and MN-major column-scaled planes), tails in M / N / K, same fp32-class bound as 3xTF32."""
+    import sliced_b200 as S
+    monkeypatch.setenv("SLICED_GEMM_CFG", "4")
+    monkeypatch.setenv("SLICED_GEMM_F16_STRICT", "1")
+    monkeypatch.setenv("SLICED_GEMM_TC_FORCE", "1")
+    ctx = S.Context(0)
+    m, n, k = shape
+    for (ta, tb) in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        rng = np.random.default_rng(m + n + k + ta * 2 + tb)
+        a, b = rng.uniform(-1, 1, m * k).astype(np.float32), rng.uniform(-1, 1, k * n).astype(np.float32)
+        t = truth(ta, tb, m, n, k, a, b)
+        got = run(ctx, ta, tb, m, n, k, a, b, S.GEMM_3XF16)
+        err = np.max(np.abs(got - t))
+        ref_err = np.max(np.abs(O.gemm_ex(ta, tb, m, n, k, a, b) - t))
+        assert err <= 4 * k * 2.0 ** -24 and err <= 16 * ref_err + 2.0 ** -22, (ta, tb, m, n, k, err, ref_err)
+        c0 = rng.uniform(-5, 5, m * n).astype(np.float32)
+        got = run(ctx, ta, tb, m, n, k, a, b, S.GEMM_3XF16, c0, True)
+        assert np.max(np.abs(got - (t + c0))) <= 4 * k * 2.0 ** -24 + 2.0 ** -21
+    ctx.close()
+
+
+def test_3xf16_scaling_is_exact_and_per_output_index(monkeypatch):
+    """Rows of A and columns of B spread over 2^-40 .. 2^40: every output element must keep fp32-class RELATIVE accuracy with
+    respect to its own row/column scale (the power-of-two scaling is per output index and exact), zero rows / columns stay
+    exactly zero, and scaling an operand by a power of two scales the result bit-exactly."""
+    import sliced_b200 as S
+    monkeypatch.setenv("SLICED_GEMM_CFG", "4")
+    monkeypatch.setenv("SLICED_GEMM_F16_STRICT", "1")
+    ctx = S.Context(0)
+    m, n, k = 512, 768, 1024
+    rng = np.random.default_rng(3)
+    ra = np.ldexp(1.0, rng.integers(-40, 40, m)).astype(np.float32)
+    cb = np.ldexp(1.0, rng.integers(-40, 40, n)).astype(np.float32)
+    a0 = rng.uniform(-1, 1, (m, k)).astype(np.float32)
+    b0 = rng.uniform(-1, 1, (k, n)).astype(np.float32)
+    a0[7] = 0
+    b0[:, 11] = 0
+    for (ta, tb) in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        a = a0 * ra[:, None]
+        b = b0 * cb[None, :]
+        am = np.ascontiguousarray(a.T if ta else a).ravel()
+        bm = np.ascontiguousarray(b.T if tb else b).ravel()
+        got = run(ctx, ta, tb, m, n, k, am, bm, S.GEMM_3XF16).reshape(m, n).astype(np.float64)
+        t = a.astype(np.float64) @ b.astype(np.float64)
+        rel = np.abs(got - t) / (ra[:, None].astype(np.float64) * cb[None, :].astype(np.float64))
+        assert np.max(rel) <= 4 * k * 2.0 ** -24, (ta, tb, np.max(rel))
+        assert np.all(got[7] == 0) and np.all(got[:, 11] == 0)
+        base = run(ctx, ta, tb, m, n, k, np.ascontiguousarray(a0.T if ta else a0).ravel(), np.ascontiguousarray(b0.T if tb else b0).ravel(),
+                   S.GEMM_3XF16).reshape(m, n)
+        assert np.array_equal(got.astype(np.float32), base * ra[:, None] * cb[None, :])
+    ctx.close()
+
+
+def test_3xf16_wide_dynamic_range_inside_a_row(monkeypatch):
+    """Elements far below their row's maximum lose low bits in fp16 (floor: 2^-40 of the row maximum); the result must still be
+    fp32-class in the norm-wise sense |err| <= c K eps max|a_i| max|b_j|."""
+    import sliced_b200 as S
+    monkeypatch.setenv("SLICED_GEMM_CFG", "4")
+    monkeypatch.setenv("SLICED_GEMM_F16_STRICT", "1")
+    ctx = S.Context(0)
+    m, n, k = 256, 512, 2048
+    rng = np.random.default_rng(9)
+    a = (rng.uniform(-1, 1, (m, k)) * np.ldexp(1.0, rng.integers(-30, 1, (m, k)))).astype(np.float32)
+    b = (rng.uniform(-1, 1, (k, n)) * np.ldexp(1.0, rng.integers(-30, 1, (k, n)))).astype(np.float32)
+    got = run(ctx, 0, 0, m, n, k, a.ravel(), b.ravel(), S.GEMM_3XF16).reshape(m, n).astype(np.float64)
+    t = a.astype(np.float64) @ b.astype(np.float64)
+    bound = 4 * k * 2.0 ** -24 * np.max(np.abs(a), axis=1)[:, None] * np.max(np.abs(b), axis=0)[None, :]
+    assert np.all(np.abs(got - t) <= bound)
+    # and against the element-wise fp32 bound  K eps sum|a||b|  (what a CPU sgemm guarantees): report, gate at 8x
+    ew = k * 2.0 ** -24 * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64))
+    ratio = np.max(np.abs(got - t) / ew)
+    print(f"3xf16 wide-range: max err / (K eps sum|a||b|) = {ratio:.3e}")
+    assert ratio <= 8
+    ctx.close()
 
 
 @pytest.mark.parametrize("kc", ["0", "1", "2", "8"])
