@@ -289,8 +289,9 @@ __global__ void __launch_bounds__(256) gemm_nt_skinny_kernel(size_t m, size_t n,
 }  // namespace
 
 // returns SL_OK when a skinny kernel handled the call, 1 when the shape is not skinny (caller falls through)
-int sl_gemm_skinny_f32(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const float* a, const float* b, float* c,
-                       int accumulate) {
+// v1 kernels: fallback of gemm_skinny.cu for the shapes its kernels do not take (unaligned, k % 4 != 0, B too large for shared memory)
+int sl_gemm_skinny_f32_v1(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const float* a, const float* b, float* c,
+                          int accumulate) {
     const size_t cap = (size_t)ctx->num_sms * 8;
     if (!trans_a && !trans_b && n <= SK_N && k >= 256 && m >= 64) {
         size_t blocks = (m + 31) / 32;

@@ -30,7 +30,7 @@
 int sl_gemm_simt(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
                  int accumulate);
 int sl_gemm_skinny_f32(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const float* a, const float* b, float* c,
-                       int accumulate);
+                       int accumulate, const float* mask_src, int* mask_done);
 
 namespace {
 
@@ -455,7 +455,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < CPW; j += 4) {
                     const int n0 = nbase + j;
-                    if (n0 >= p.N) break;
+                    if (n0 >= p.N) continue;
                     if (p.c_vec_ok && n0 + 4 <= p.N) {
                         epilogue_store4(p, crow, (size_t)row * p.N, n0, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
                     } else {
@@ -547,6 +547,53 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
                  : "memory");
 }
 
+// ---- coalesced epilogue.  tcgen05.ld hands every thread one accumulator ROW, so storing straight from registers makes each
+// warp-wide STG touch 32 different rows = 32 cache lines (measured: the store phase, not the MMAs, bounded the K = 4096 gemms at
+// 75 % tensor-pipe activity).  Instead each warp bounces 32 x 32 blocks through a private 4 KB shared-memory tile (16-byte chunks
+// XOR-swizzled by row so both the row-owner and the coalesced access pattern are conflict-free): global accesses then cover
+// 4 rows x 128 contiguous bytes per instruction.
+__device__ __forceinline__ int epi_slot(int r, int ch) { return r * 32 + ((ch ^ (r & 7)) << 2); }
+// registers (lane = row, v[32] = 32 consecutive columns)  ->  dst[(row_base + r) * ld + col0 + c], rows < rows_valid, cols < cols_valid (multiple of 4)
+__device__ __forceinline__ void epi_scatter(float* stage, int lane, const float (&v)[32], float* dst, size_t ld, int rows_valid, int cols_valid) {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<float4*>(stage + epi_slot(lane, ch)) = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+    __syncwarp();
+    const int ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        const float4 x = *reinterpret_cast<const float4*>(stage + epi_slot(r, ch));
+        if (r < rows_valid && ch * 4 < cols_valid) *reinterpret_cast<float4*>(dst + (size_t)r * ld + ch * 4) = x;
+    }
+    __syncwarp();
+}
+// the reverse: src tile -> the row-owning lane, combined into v[32] on the fly (MASK: v *= (src >= 0); else v += src); out-of-range
+// elements read as 0.  The read-back applies chunk by chunk so no second 32-register array is live (the kernel is capped at 168).
+template <bool MASK>
+__device__ __forceinline__ void epi_gather(float* stage, int lane, float (&v)[32], const float* src, size_t ld, int rows_valid, int cols_valid) {
+    const int ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_valid && ch * 4 < cols_valid) x = *reinterpret_cast<const float4*>(src + (size_t)r * ld + ch * 4);
+        *reinterpret_cast<float4*>(stage + epi_slot(r, ch)) = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 x = *reinterpret_cast<const float4*>(stage + epi_slot(lane, c));
+        if (MASK) {
+            v[c * 4] = (x.x >= 0.f ? 1.f : 0.f) * v[c * 4]; v[c * 4 + 1] = (x.y >= 0.f ? 1.f : 0.f) * v[c * 4 + 1];
+            v[c * 4 + 2] = (x.z >= 0.f ? 1.f : 0.f) * v[c * 4 + 2]; v[c * 4 + 3] = (x.w >= 0.f ? 1.f : 0.f) * v[c * 4 + 3];
+        } else {
+            v[c * 4] += x.x; v[c * 4 + 1] += x.y; v[c * 4 + 2] += x.z; v[c * 4 + 3] += x.w;
+        }
+    }
+    __syncwarp();
+}
+
 // KIND 0: tf32 planes (4-byte elements, 32 k per 128-byte row, MMA K = 8); KIND 1: fp16 planes (64 k per row, MMA K = 16)
 template <int TERMS, int STAGES, int KIND = 0>
 struct Gemm2Cfg {
@@ -559,13 +606,14 @@ struct Gemm2Cfg {
     static constexpr int PLANES = TERMS == 3 ? 2 : 1;
     static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
     static constexpr int TMEM_COLS = 2 * TILE_N;           // two chunk buffers of 256 fp32 columns
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;   // one 32 x 32 fp32 transposition tile per epilogue warp
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_STAGE_BYTES;
     static constexpr int COLS_PER_WARP = TILE_N / (EPI_WARPS / 4);
     static_assert(SMEM_BYTES <= 227 * 1024, "stage ring does not fit in shared memory");
 };
 
 template <int TERMS, int STAGES, bool A_MN, bool B_MN, int KIND>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)   // 10 warps -> 3 on one SM sub-partition -> 168 registers
 gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
     using Cfg = Gemm2Cfg<TERMS, STAGES, KIND>;
@@ -780,14 +828,58 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                 if (lane == 0) mbar_arrive_cluster(mapa_shared(tmem_empty_bar(buf), 0));  // the leader's barrier
             }
             const int row = m_blk * Cfg::TILE_M + (int)rank * 128 + quad * 32 + lane;
-            if (row < p.M) {
+            if (p.c_vec_ok) {
+                // coalesced path: 32 x 32 blocks through the warp's shared-memory tile
+                float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + ew * 1024;
+                const int row_base = row - lane;
+                const int rows_valid = p.M - row_base;     // may be <= 0 or > 32: the helpers compare r < rows_valid
+                const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.f;
+                const size_t tile_off = (size_t)row_base * p.N;
+                float* cbase = p.C + (size_t)split * p.M * p.N + tile_off;
+#pragma unroll
+                for (int c = 0; c < CPW / 32; ++c) {
+                    const int n0 = n_blk * Cfg::TILE_N + col0 + c * 32;
+                    const int cols_valid = p.N - n0;
+                    if (cols_valid <= 0 || rows_valid <= 0) continue;   // warp-uniform (no break: keeps acc[] statically indexed)
+                    float(&v)[32] = *reinterpret_cast<float(*)[32]>(&acc[c * 32]);   // in place: acc is dead after the store
+                    if (p.col_scale) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (j < cols_valid) {
+                                const float4 cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0 + j));
+                                v[j] = (v[j] * rs) * cs.x; v[j + 1] = (v[j + 1] * rs) * cs.y;
+                                v[j + 2] = (v[j + 2] * rs) * cs.z; v[j + 3] = (v[j + 3] * rs) * cs.w;
+                            }
+                    }
+                    if (p.accumulate) epi_gather<false>(stage, lane, v, cbase + n0, (size_t)p.N, rows_valid, cols_valid);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (j < cols_valid) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                            }
+                    }
+                    if (p.mask_src) epi_gather<true>(stage, lane, v, p.mask_src + tile_off + n0, (size_t)p.N, rows_valid, cols_valid);
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = (v[j] >= 0.f ? 1.f : 0.f) * v[j];
+                    }
+                    epi_scatter(stage, lane, v, cbase + n0, (size_t)p.N, rows_valid, cols_valid);
+                    if (p.C2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = (v[j] >= 0.f ? 1.f : 0.f) * v[j];
+                        epi_scatter(stage, lane, v, p.C2 + tile_off + n0, (size_t)p.N, rows_valid, cols_valid);
+                    }
+                }
+            } else if (row < p.M) {
                 float* crow = p.C + (size_t)split * p.M * p.N + (size_t)row * p.N;
                 const int nbase = n_blk * Cfg::TILE_N + col0;
                 const float rs = p.row_scale ? __ldg(p.row_scale + row) : 1.f;
 #pragma unroll
                 for (int j = 0; j < CPW; j += 4) {
                     const int n0 = nbase + j;
-                    if (n0 >= p.N) break;
+                    if (n0 >= p.N) continue;
                     if (p.c_vec_ok && n0 + 4 <= p.N) {
                         epilogue_store4(p, crow, (size_t)row * p.N, n0, make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]), rs);
                     } else {
@@ -1391,14 +1483,16 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
     if (dtype != SL_F32 || mode == SL_GEMM_SIMT || !tc_eligible(m, n, k)) {
         if (epi.any() && dtype != SL_F32) return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "fused epilogue is f32 only");
         int rc = 1;
+        int mask_done = 0;
         if (dtype == SL_F32 && mode != SL_GEMM_SIMT)  // HBM-bound skinny shapes (n <= 16 or k <= 16) have their own kernels
-            rc = sl_gemm_skinny_f32(ctx, trans_a, trans_b, m, n, k, (const float*)a, (const float*)b, (float*)c, accumulate);
+            rc = sl_gemm_skinny_f32(ctx, trans_a, trans_b, m, n, k, (const float*)a, (const float*)b, (float*)c, accumulate, epi.mask_src, &mask_done);
         if (rc > 0) rc = sl_gemm_simt(ctx, dtype, trans_a, trans_b, m, n, k, a, b, c, accumulate);
         if (rc != SL_OK || !epi.any()) return rc;
+        if (mask_done && !bias && !relu && !epi.c2) return SL_OK;   // the skinny kernel already applied the only epilogue term
         const size_t total = m * n;
         const size_t cap = (size_t)ctx->num_sms * 8;
         size_t blocks = (total + 255) / 256;
-        SL_LAUNCH(ctx, epilogue_pass_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, total, n, (float*)c, bias, relu, epi.c2, epi.mask_src);
+        SL_LAUNCH(ctx, epilogue_pass_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, total, n, (float*)c, bias, relu, epi.c2, mask_done ? nullptr : epi.mask_src);
         return SL_OK;
     }
     // 3xFP16: needs the 2-CTA kernel and 16-byte aligned fp16 rows in whatever layout the operand already has; anything else

@@ -329,7 +329,11 @@ def test_full_size_sampled(ctx, mode):
 
 @pytest.mark.parametrize("case", [("NN", 0, 0, 1000, 10, 4096), ("NN", 0, 0, 257, 16, 300), ("NN", 0, 0, 4096, 1, 1000),
                                   ("TN", 1, 0, 512, 10, 8192), ("TN", 1, 0, 1030, 7, 5000), ("TN", 1, 0, 4096, 10, 2048),
-                                  ("NT", 0, 1, 1000, 512, 10), ("NT", 0, 1, 333, 1026, 16), ("NT", 0, 1, 64, 64, 3)],
+                                  ("NT", 0, 1, 1000, 512, 10), ("NT", 0, 1, 333, 1026, 16), ("NT", 0, 1, 64, 64, 3),
+                                  # odd small extents (zero-padded column), B too large for shared memory (v1 fallback), ragged row tails
+                                  ("NN", 0, 0, 1001, 7, 512), ("NN", 0, 0, 300, 16, 16384), ("NN", 0, 0, 8200, 10, 4096),
+                                  ("TN", 1, 0, 1028, 7, 5000), ("TN", 1, 0, 4096, 10, 65536), ("NT", 0, 1, 777, 1028, 9),
+                                  ("NT", 0, 1, 5000, 4096, 10)],
                          ids=lambda c: f"{c[0]}-{c[3]}x{c[4]}x{c[5]}")
 def test_skinny_shapes(case, monkeypatch):
     """the HBM-bound skinny kernels (the 10-class head of the nn.rs MLP): fp32 FMA accumulation, K-scaled tolerance"""
