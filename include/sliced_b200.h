@@ -226,6 +226,14 @@ int sl_gemm_ex(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_
 int sl_gemm_grad(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs,
                  void* lhs_grad, void* rhs_grad, const void* out_grad, int accumulate, int mode);
 
+/* Fused Linear backward w.r.t. the parameters: w_grad[k x n] = lhs[m x k]^T * out_grad[m x n] (SET, like sl_gemm_grad's rhs half) and
+ * b_grad[n] += column sums of out_grad (sl_add_row_mut_grad).  In 3xFP16 mode the pass over out_grad that finds its per-column
+ * scales also produces the column sums, so the bias gradient costs no extra read of out_grad.  b_grad may be NULL.
+ * ref: src/ops2/gemm/grad.rs:29-36 (rhs_grad) + src/ops2/row_op/cpu.rs:41-48 (add_row_mut_grad), i.e. the two tape closures a
+ * `Linear::forward` (examples/nn.rs:40-46) leaves behind for its parameters. */
+int sl_linear_bwd_params(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* out_grad, void* w_grad, void* b_grad,
+                         int mode);
+
 /* Operand-plane reuse scope for the tensor-core gemm.  Every f32 gemm first derives TF32 hi/lo planes from its operands; between
  * begin and end those planes are kept and reused by later gemms that read the SAME buffer (same pointer and size) — e.g. an
  * activation in its forward gemm and again in the weight-gradient gemm of the same training step.  Contract: a buffer that has

@@ -33,6 +33,10 @@ struct sl_ctx {
     std::vector<PlaneEntry> plane_cache;
     size_t plane_cursor = 0;
     bool plane_scope = false;
+    // per-column power-of-two scales of a buffer, a by-product of splitting it row-wise (3xFP16 mode), reused inside the scope
+    struct ColScale { const void* src; size_t rows, cols; float* scale; float* inv; size_t cap; bool valid; };
+    std::vector<ColScale> colscale_cache;
+    size_t colscale_cursor = 0;
     // second stream for host->device prefetch (sl_write_prefetch), created lazily
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_done = nullptr, compute_done = nullptr;

@@ -108,6 +108,8 @@ int sl_ctx_destroy(sl_ctx* ctx) {
         if (e.hi) cudaFree(e.hi);
         if (e.lo) cudaFree(e.lo);
     }
+    for (auto& e : ctx->colscale_cache)
+        if (e.scale) cudaFree(e.scale);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ws2) cudaFree(ctx->ws2);
     if (ctx->copy_stream) {

@@ -215,6 +215,8 @@ struct GemmParams {
     const float* mask_src;  // optional [M x N]: v *= (mask_src >= 0) before the store (fused relu gradient)
     const float* row_scale; // 3xFP16 mode: acc is multiplied by row_scale[row] * col_scale[col] (exact powers of two undoing the
     const float* col_scale; //   operand scaling) before anything else; both NULL otherwise
+    int kc_first;           // 2-CTA kernel: k-blocks of the FIRST TWO chunks of every tile (>= kc_blocks; see the kernel)
+    int debug;              // bit 0: skip the final store (timing experiments only, SLICED_GEMM_DEBUG)
 };
 
 // shared epilogue arithmetic of both MMA kernels: 4 consecutive columns of one output row
@@ -668,6 +670,13 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     const int num_tiles = num_m * num_n;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
     const int kc = p.kc_blocks > 0 ? p.kc_blocks : num_kb;
+    // Chunk schedule of one work unit.  While the epilogue warps store a finished tile they cannot drain TMEM, so the MMA warp can
+    // only run two chunks into the next tile before it stalls: the first two chunks of every unit are therefore longer (kc_first
+    // k-blocks) than the rest (kc), buying the store phase 2 * kc_first k-blocks of MMA time at the cost of two slightly longer
+    // round-toward-zero chains per tile.
+    const int kcf = p.kc_first > kc ? p.kc_first : kc;
+    auto chunk_begin = [&](int ch) { return ch < 2 ? ch * kcf : 2 * kcf + (ch - 2) * kc; };
+    auto chunk_count = [&](int nkb) { return nkb <= 2 * kcf ? (nkb + kcf - 1) / kcf : 2 + (nkb - 2 * kcf + kc - 1) / kc; };
     // split-K: a work unit is (tile, split); split s covers k-blocks [s*kbs, (s+1)*kbs) and writes its partial tile to
     // C + s*M*N (the host points C at scratch and folds the partials in order afterwards)
     const int splits = p.splits > 0 ? p.splits : 1;
@@ -749,14 +758,14 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             uint32_t g = 0;
             for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
                 const int kb0 = (unit % splits) * kbs, kb1 = min(num_kb, kb0 + kbs);
-                const int num_chunks = (kb1 - kb0 + kc - 1) / kc;
+                const int num_chunks = chunk_count(kb1 - kb0);
                 for (int ch = 0; ch < num_chunks; ++ch, ++g) {
                     const uint32_t buf = g & 1;
                     mbar_wait(tmem_empty_bar(buf), ((g >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + buf * Cfg::TILE_N;
-                    const int kb_begin = kb0 + ch * kc;
-                    const int kb_end = min(kb1, kb_begin + kc);
+                    const int kb_begin = kb0 + chunk_begin(ch);
+                    const int kb_end = min(kb1, kb0 + chunk_begin(ch + 1));
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
@@ -803,7 +812,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             tile_coords(unit / splits, m_blk, n_blk);
             const int split = unit % splits;
             const int kb0 = split * kbs, kb1 = min(num_kb, kb0 + kbs);
-            const int num_chunks = (kb1 - kb0 + kc - 1) / kc;
+            const int num_chunks = chunk_count(kb1 - kb0);
             float acc[CPW];
             for (int ch = 0; ch < num_chunks; ++ch, ++g) {
                 const uint32_t buf = g & 1;
@@ -828,6 +837,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                 if (lane == 0) mbar_arrive_cluster(mapa_shared(tmem_empty_bar(buf), 0));  // the leader's barrier
             }
             const int row = m_blk * Cfg::TILE_M + (int)rank * 128 + quad * 32 + lane;
+            if (p.debug & 1) continue;
             if (p.c_vec_ok) {
                 // coalesced path: 32 x 32 blocks through the warp's shared-memory tile
                 float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + ew * 1024;
@@ -1012,12 +1022,17 @@ __device__ __forceinline__ void split4_store(const float4& v, float sx, float sy
 
 // K-contiguous operand [R x K] (K % 4 == 0): one block per row.  Rows of up to 8192 elements are held in registers between the
 // max pass and the split pass (one HBM read); longer rows are re-read (L2).
+// colmax_partial (optional, register-cached rows only): [gridDim.x][K] running max |x| per column over the rows this block handled —
+// the column scales the same buffer needs when it is later used with the other index contracted (weight-gradient gemm).
 __global__ void __launch_bounds__(256) prep16_rows_kernel(size_t R, size_t K, const float* __restrict__ src, __half* __restrict__ hi,
-                                                          __half* __restrict__ lo, float* __restrict__ scale_inv) {
+                                                          __half* __restrict__ lo, float* __restrict__ scale_inv, float* __restrict__ colmax_partial) {
     __shared__ float red[8];
     __shared__ float bcast;
     const size_t nv = K / 4;
     const bool cached = nv <= 8 * 256;
+    float4 cm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (size_t row = blockIdx.x; row < R; row += gridDim.x) {
         const float4* s4 = reinterpret_cast<const float4*>(src + row * K);
         float4 v[8];
@@ -1029,6 +1044,10 @@ __global__ void __launch_bounds__(256) prep16_rows_kernel(size_t R, size_t K, co
                 if (idx < nv) {
                     v[i] = __ldg(s4 + idx);
                     m = absmax4(m, v[i]);
+                    if (colmax_partial) {
+                        cm[i].x = fmaxf(cm[i].x, fabsf(v[i].x)); cm[i].y = fmaxf(cm[i].y, fabsf(v[i].y));
+                        cm[i].z = fmaxf(cm[i].z, fabsf(v[i].z)); cm[i].w = fmaxf(cm[i].w, fabsf(v[i].w));
+                    }
                 }
             }
         } else {
@@ -1061,26 +1080,39 @@ __global__ void __launch_bounds__(256) prep16_rows_kernel(size_t R, size_t K, co
         }
         __syncthreads();
     }
+    if (colmax_partial && cached) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const size_t idx = threadIdx.x + (size_t)i * 256;
+            if (idx < nv) *reinterpret_cast<float4*>(colmax_partial + (size_t)blockIdx.x * K + idx * 4) = cm[i];
+        }
+    }
 }
 
 // MN-contiguous operand [K x R] (R % 4 == 0), scale per column r over all K rows.
 // pass 1: grid (column blocks of 1024, slabs of rows) -> partial[slab][R] = max |x| over the slab
+// partial_sum (optional): the same pass also produces the slab's column SUMS (sl_linear_bwd_params: bias gradient).
 __global__ void __launch_bounds__(256) prep16_colmax_kernel(size_t K, size_t R, size_t rows_per_slab, const float* __restrict__ src,
-                                                            float* __restrict__ partial) {
+                                                            float* __restrict__ partial, float* __restrict__ partial_sum) {
     const size_t c = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
     if (c >= R) return;
     const size_t k0 = (size_t)blockIdx.y * rows_per_slab;
     const size_t k1 = k0 + rows_per_slab < K ? k0 + rows_per_slab : K;
-    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (size_t k = k0; k < k1; ++k) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(src + k * R + c));
         m.x = fmaxf(m.x, fabsf(v.x)); m.y = fmaxf(m.y, fabsf(v.y)); m.z = fmaxf(m.z, fabsf(v.z)); m.w = fmaxf(m.w, fabsf(v.w));
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
     }
     *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * R + c) = m;
+    if (partial_sum) *reinterpret_cast<float4*>(partial_sum + (size_t)blockIdx.y * R + c) = sum;
 }
 // pass 2: fold the slabs -> scale[r], scale_inv[r]
+//         (and the slab sums, in slab order -> sum_acc[r] += total: deterministic)
 __global__ void __launch_bounds__(256) prep16_colscale_kernel(size_t R, int slabs, const float* __restrict__ partial, float* __restrict__ scale,
-                                                              float* __restrict__ scale_inv) {
+                                                              float* __restrict__ scale_inv, const float* __restrict__ partial_sum,
+                                                              float* __restrict__ sum_acc) {
     const size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= R) return;
     float m = 0.f;
@@ -1088,6 +1120,11 @@ __global__ void __launch_bounds__(256) prep16_colscale_kernel(size_t R, int slab
     float inv;
     scale[r] = scale_for_max(m, &inv);
     scale_inv[r] = inv;
+    if (partial_sum) {
+        float t = 0.f;
+        for (int s = 0; s < slabs; ++s) t += partial_sum[(size_t)s * R + r];
+        sum_acc[r] += t;
+    }
 }
 // pass 3: element-wise split with the column's scale (planes keep the [K x R] layout)
 __global__ void __launch_bounds__(256) prep16_cols_kernel(size_t K, size_t R, const float* __restrict__ src, const float* __restrict__ scale,
@@ -1269,11 +1306,13 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu; p.C2 = c2; p.mask_src = mask_src;
     p.row_scale = row_scale; p.col_scale = col_scale;
+    p.debug = env_int("SLICED_GEMM_DEBUG", 0);
     p.c_vec_ok = (N % 4 == 0) && sl_aligned16(C) && (!bias || sl_aligned16(bias)) && (!c2 || sl_aligned16(c2)) && (!mask_src || sl_aligned16(mask_src)) &&
                  (!col_scale || sl_aligned16(col_scale));
     const bool three = a_lo != nullptr;
     // K-chunk (in k-blocks of 32) accumulated inside TMEM before promotion to fp32 registers; 0 = whole K (TF32 fast mode)
     p.kc_blocks = three ? env_int("SLICED_GEMM_KC", 4) : env_int("SLICED_GEMM_KC_TF32", 0);
+    p.kc_first = three ? env_int("SLICED_GEMM_KC_FIRST", 8) : 0;
     // tile configuration: SLICED_GEMM_CFG = 0 auto | 1: 128x256x32 | 2: 128x256x16 (swizzle 64B, deeper ring) | 3: 128x128x32
     //                                       | 4: 2-CTA pairs (cta_group::2), 256x256x32 per pair
     const int cfg = sl_gemm_pick_cfg(ctx, M, N);
@@ -1416,36 +1455,84 @@ __global__ void __launch_bounds__(256) epilogue_pass_kernel(size_t total, size_t
     }
 }
 
+// Column-scale reuse inside a gemm scope: when a [rows x cols] buffer is split with its ROWS as the output index (contraction over
+// the columns), the same pass also yields max |x| per COLUMN for free; those are exactly the scales the buffer needs when a later
+// gemm of the scope contracts over its rows instead (activation: forward gemm, then weight-gradient gemm).
+static sl_ctx::ColScale* colscale_find(sl_ctx* ctx, const void* src, size_t rows, size_t cols) {
+    for (auto& e : ctx->colscale_cache)
+        if (e.valid && e.src == src && e.rows == rows && e.cols == cols) return &e;
+    return nullptr;
+}
+static int colscale_new(sl_ctx* ctx, const void* src, size_t rows, size_t cols, sl_ctx::ColScale** out) {
+    if (ctx->colscale_cursor >= ctx->colscale_cache.size()) ctx->colscale_cache.push_back(sl_ctx::ColScale{nullptr, 0, 0, nullptr, nullptr, 0, false});
+    sl_ctx::ColScale& e = ctx->colscale_cache[ctx->colscale_cursor++];
+    if (e.cap < cols) {
+        SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (e.scale) cudaFree(e.scale);
+        e.scale = nullptr;
+        SL_CUDA(ctx, cudaMalloc((void**)&e.scale, 2 * cols * sizeof(float)));
+        e.cap = cols;
+    }
+    e.inv = e.scale + cols;
+    e.src = src; e.rows = rows; e.cols = cols; e.valid = true;
+    *out = &e;
+    return SL_OK;
+}
+
 // 3xFP16 path: scale + split both operands into fp16 hi / lo planes IN THEIR OWN LAYOUT (K-major or MN-major, never transposed)
 // and run the kind::f16 2-CTA kernel; the epilogue undoes the scaling.
+// *inv_out receives the [mn] vector of inverse scales the epilogue needs (scale_inv, or a cached one).
+// colsum_acc (MN-major operand only): colsum_acc[j] += sum over k of src[k][j], computed in the same pass as the column maxima.
 static int prep16_operand(sl_ctx* ctx, const float* src, size_t mn, size_t k, bool k_contiguous, __half* hi, __half* lo, float* scale,
-                          float* scale_inv) {
+                          float* scale_inv, const float** inv_out, float* colsum_acc) {
     const size_t cap = (size_t)ctx->num_sms * 8;
+    *inv_out = scale_inv;
     if (k_contiguous) {  // [mn x k]
-        SL_LAUNCH(ctx, prep16_rows_kernel, (unsigned)(mn < cap * 4 ? mn : cap * 4), 256, 0, mn, k, src, hi, lo, scale_inv);
+        if (ctx->plane_scope && k <= 8192 && mn >= 4 * cap && !colscale_find(ctx, src, mn, k)) {
+            const unsigned grid = (unsigned)cap;
+            void* partial = nullptr;
+            int rc = sl_ws_reserve(ctx, (size_t)grid * k * sizeof(float), &partial);
+            if (rc != SL_OK) return rc;
+            sl_ctx::ColScale* e = nullptr;
+            if ((rc = colscale_new(ctx, src, mn, k, &e)) != SL_OK) return rc;
+            SL_LAUNCH(ctx, prep16_rows_kernel, grid, 256, 0, mn, k, src, hi, lo, scale_inv, (float*)partial);
+            SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((k + 255) / 256), 256, 0, k, (int)grid, (const float*)partial, e->scale, e->inv,
+                      (const float*)nullptr, (float*)nullptr);
+            return SL_OK;
+        }
+        SL_LAUNCH(ctx, prep16_rows_kernel, (unsigned)(mn < cap * 4 ? mn : cap * 4), 256, 0, mn, k, src, hi, lo, scale_inv, (float*)nullptr);
         return SL_OK;
     }
-    // [k x mn]: column maxima in two deterministic passes, then the element-wise split
-    const size_t col_blocks = (mn / 4 + 255) / 256;
-    size_t slabs = cap / col_blocks;
-    if (slabs < 1) slabs = 1;
-    if (slabs > (k + 31) / 32) slabs = (k + 31) / 32;   // at least 32 rows per slab
-    if (slabs > 65535) slabs = 65535;
-    const size_t rows_per_slab = (k + slabs - 1) / slabs;
-    slabs = (k + rows_per_slab - 1) / rows_per_slab;
-    void* partial = nullptr;
-    int rc = sl_ws_reserve(ctx, slabs * mn * sizeof(float), &partial);
-    if (rc != SL_OK) return rc;
-    SL_LAUNCH(ctx, prep16_colmax_kernel, dim3((unsigned)col_blocks, (unsigned)slabs, 1), 256, 0, k, mn, rows_per_slab, src, (float*)partial);
-    SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((mn + 255) / 256), 256, 0, mn, (int)slabs, (const float*)partial, scale, scale_inv);
+    // [k x mn]: column maxima in two deterministic passes (or from the scope cache), then the element-wise split
+    const float* use_scale = scale;
+    sl_ctx::ColScale* hit = (ctx->plane_scope && !colsum_acc) ? colscale_find(ctx, src, k, mn) : nullptr;
+    if (hit) {
+        use_scale = hit->scale;
+        *inv_out = hit->inv;
+    } else {
+        const size_t col_blocks = (mn / 4 + 255) / 256;
+        size_t slabs = cap / col_blocks;
+        if (slabs < 1) slabs = 1;
+        if (slabs > (k + 31) / 32) slabs = (k + 31) / 32;   // at least 32 rows per slab
+        if (slabs > 65535) slabs = 65535;
+        const size_t rows_per_slab = (k + slabs - 1) / slabs;
+        slabs = (k + rows_per_slab - 1) / rows_per_slab;
+        void* partial = nullptr;
+        int rc = sl_ws_reserve(ctx, (colsum_acc ? 2 : 1) * slabs * mn * sizeof(float), &partial);
+        if (rc != SL_OK) return rc;
+        float* psum = colsum_acc ? (float*)partial + slabs * mn : nullptr;
+        SL_LAUNCH(ctx, prep16_colmax_kernel, dim3((unsigned)col_blocks, (unsigned)slabs, 1), 256, 0, k, mn, rows_per_slab, src, (float*)partial, psum);
+        SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((mn + 255) / 256), 256, 0, mn, (int)slabs, (const float*)partial, scale, scale_inv,
+                  (const float*)psum, colsum_acc);
+    }
     const size_t total = k * (mn / 4);
     size_t blocks = (total + 255) / 256;
-    SL_LAUNCH(ctx, prep16_cols_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, k, mn, src, (const float*)scale, hi, lo);
+    SL_LAUNCH(ctx, prep16_cols_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, k, mn, src, use_scale, hi, lo);
     return SL_OK;
 }
 
 static int gemm_f16x3(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const float* a, const float* b, float* c, int accumulate,
-                      const Epi& epi) {
+                      const Epi& epi, float* b_colsum_acc = nullptr) {
     const bool a_kc = !trans_a, b_kc = trans_b != 0;
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t a_plane = up(m * k * 2), b_plane = up(n * k * 2), sm = up(m * 4), sn = up(n * 4);
@@ -1460,10 +1547,15 @@ static int gemm_f16x3(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n,
     float* a_inv = (float*)((char*)a_sc + sm);
     float* b_sc = (float*)((char*)a_inv + sm);
     float* b_inv = (float*)((char*)b_sc + sn);
-    if ((rc = prep16_operand(ctx, a, m, k, a_kc, a_hi, a_lo, a_sc, a_inv)) != SL_OK) return rc;
-    if ((rc = prep16_operand(ctx, b, n, k, b_kc, b_hi, b_lo, b_sc, b_inv)) != SL_OK) return rc;
+    const float *a_inv_use = nullptr, *b_inv_use = nullptr;
+    if ((rc = prep16_operand(ctx, a, m, k, a_kc, a_hi, a_lo, a_sc, a_inv, &a_inv_use, nullptr)) != SL_OK) return rc;
+    if ((rc = prep16_operand(ctx, b, n, k, b_kc, b_hi, b_lo, b_sc, b_inv, &b_inv_use, b_kc ? nullptr : b_colsum_acc)) != SL_OK) return rc;
     return sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, a_kc ? k : m, b_hi, b_lo, b_kc ? k : n, c, epi.bias, accumulate, epi.relu, epi.c2,
-                             epi.mask_src, a_kc ? 0 : 1, b_kc ? 0 : 1, 1, a_inv, b_inv);
+                             epi.mask_src, a_kc ? 0 : 1, b_kc ? 0 : 1, 1, a_inv_use, b_inv_use);
+}
+
+static bool f16x3_eligible(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b) {
+    return sl_gemm_pick_cfg(ctx, m, n) == 4 && ((trans_a ? m : k) % 8 == 0) && ((trans_b ? k : n) % 8 == 0) && sl_aligned16(a) && sl_aligned16(b);
 }
 
 static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
@@ -1479,6 +1571,9 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
     // a gemm that overwrites a buffer whose planes are cached makes them stale
     if (ctx->plane_scope)
         for (auto& e : ctx->plane_cache)
+            if (e.valid && (e.src == c || e.src == (const void*)epi.c2)) e.valid = false;
+    if (ctx->plane_scope)
+        for (auto& e : ctx->colscale_cache)
             if (e.valid && (e.src == c || e.src == (const void*)epi.c2)) e.valid = false;
     if (dtype != SL_F32 || mode == SL_GEMM_SIMT || !tc_eligible(m, n, k)) {
         if (epi.any() && dtype != SL_F32) return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "fused epilogue is f32 only");
@@ -1498,8 +1593,7 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
     // 3xFP16: needs the 2-CTA kernel and 16-byte aligned fp16 rows in whatever layout the operand already has; anything else
     // takes the 3xTF32 path below (same accuracy class, half the tensor-pipe rate).
     if (mode == SL_GEMM_3XF16) {
-        const bool ok = sl_gemm_pick_cfg(ctx, m, n) == 4 && ((trans_a ? m : k) % 8 == 0) && ((trans_b ? k : n) % 8 == 0) && sl_aligned16(a) &&
-                        sl_aligned16(b);
+        const bool ok = f16x3_eligible(ctx, trans_a, trans_b, m, n, k, a, b);
         if (ok) return gemm_f16x3(ctx, trans_a, trans_b, m, n, k, (const float*)a, (const float*)b, (float*)c, accumulate, epi);
         if (env_int("SLICED_GEMM_F16_STRICT", 0))   // tests: make the silent 3xTF32 substitution visible
             return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "3xFP16 path cannot take %zux%zux%zu (trans %d,%d)", m, n, k, trans_a, trans_b);
@@ -1610,10 +1704,38 @@ int sl_linear_bwd_input_relu(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t 
     return gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, x_grad, 0, mode, e);
 }
 
+int sl_add_row_mut_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* rhs_grad, const void* out_grad);
+
+int sl_linear_bwd_params(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* out_grad, void* w_grad, void* b_grad,
+                         int mode) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (m == 0 || k == 0 || n == 0) return SL_OK;
+    SL_REQUIRE(ctx, lhs && out_grad && w_grad, "NULL argument");
+    if (mode < 0) mode = ctx->gemm_mode;
+    // the weight-gradient gemm contracts over the batch: out_grad is its MN-major B operand, whose column maxima need one full
+    // pass over out_grad anyway — that pass also produces the bias gradient's column sums
+    if (b_grad && dtype == SL_F32 && mode == SL_GEMM_3XF16 && tc_eligible(k, n, m) && f16x3_eligible(ctx, 1, 0, k, n, m, lhs, out_grad)) {
+        if (ctx->plane_scope) {
+            for (auto& e : ctx->colscale_cache)
+                if (e.valid && e.src == w_grad) e.valid = false;
+            for (auto& e : ctx->plane_cache)
+                if (e.valid && e.src == w_grad) e.valid = false;
+        }
+        return gemm_f16x3(ctx, 1, 0, k, n, m, (const float*)lhs, (const float*)out_grad, (float*)w_grad, 0, Epi{}, (float*)b_grad);
+    }
+    if (b_grad) {
+        int rc = sl_add_row_mut_grad(ctx, dtype, m, n, b_grad, out_grad);
+        if (rc != SL_OK) return rc;
+    }
+    return gemm_ex_impl(ctx, dtype, 1, 0, k, n, m, lhs, out_grad, w_grad, 0, mode, Epi{});
+}
+
 int sl_gemm_scope_begin(sl_ctx* ctx) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     for (auto& e : ctx->plane_cache) e.valid = false;
+    for (auto& e : ctx->colscale_cache) e.valid = false;
     ctx->plane_cursor = 0;
+    ctx->colscale_cursor = 0;
     ctx->plane_scope = true;
     return SL_OK;
 }
@@ -1621,6 +1743,7 @@ int sl_gemm_scope_begin(sl_ctx* ctx) {
 int sl_gemm_scope_end(sl_ctx* ctx) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     for (auto& e : ctx->plane_cache) e.valid = false;
+    for (auto& e : ctx->colscale_cache) e.valid = false;
     ctx->plane_scope = false;
     return SL_OK;
 }

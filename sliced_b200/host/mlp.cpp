@@ -177,8 +177,9 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
     for (size_t li = L; li-- > 0;) {
         const size_t I = dims_[li], O = dims_[li + 1];
         const void* lin = li == 0 ? x->dptr : a_[li - 1]->dptr;
-        d.check(sl_add_row_mut_grad(c, SL_F32, batch, O, d.grad(layers_[li].bias.data)->dptr, gz_[li]->dptr));   // b.grad += colsum
-        d.check(sl_gemm_tn(c, SL_F32, I, O, batch, lin, gz_[li]->dptr, d.grad(layers_[li].weights.data)->dptr, -1));  // Tgemm(k,n,m,lhs,og,W.grad) SET
+        // b.grad += colsum(gz) ; W.grad = Tgemm(k,n,m,lhs,og) SET — one entry point so that gz is read once for both
+        d.check(sl_linear_bwd_params(c, SL_F32, batch, I, O, lin, gz_[li]->dptr, d.grad(layers_[li].weights.data)->dptr,
+                                     d.grad(layers_[li].bias.data)->dptr, -1));
         // data-parallel: this layer's gradients are final -> start their sum all-reduce on the communication stream while the
         // remaining layers' backward gemms keep the tensor cores busy (no-op for a world of one)
         d.check(sl_allreduce_sum_async(c, SL_F32, (float*)bucket_->dptr + seg_off_[2 * li], seg_off_[2 * li + 2] - seg_off_[2 * li]));

@@ -158,6 +158,71 @@ def test_fused_entry_points_equal_composition():
     ctx.close()
 
 
+@pytest.mark.parametrize("shape", [(512, 384, 640), (1000, 4096, 10), (4096, 2048, 2560), (8192, 1024, 1280)], ids=lambda t: "x".join(map(str, t)))
+@pytest.mark.parametrize("scoped", [False, True])
+def test_linear_bwd_params_equals_composition(shape, scoped):
+    """sl_linear_bwd_params == sl_gemm_tn (weights: bit-identical, same planes and scales) + sl_add_row_mut_grad (bias: same column
+    sums in a different deterministic order -> K-scaled tolerance), with and without a gemm scope (inside a scope the column scales
+    of lhs come from the earlier row-wise split of the forward gemm)."""
+    import sliced_b200 as S
+    ctx = S.Context(0)
+    L = ctx.lib
+    m, k, n = shape
+    rng = np.random.default_rng(m + k + n)
+    lhs = ctx.array(rng.uniform(-1, 1, m * k).astype(np.float32))
+    og_h = rng.uniform(-1, 1, m * n).astype(np.float32)
+    og = ctx.array(og_h)
+    w_ref = ctx.gemm_tn(k, n, m, lhs, og)
+    b0 = rng.uniform(-1, 1, n).astype(np.float32)
+    b_ref = ctx.array(b0)
+    ctx.add_row_mut_grad(m, n, b_ref, og)
+    if scoped:
+        ctx.gemm_scope_begin()
+        wfwd = ctx.array(rng.uniform(-1, 1, k * n).astype(np.float32))
+        ctx.gemm(m, k, n, lhs, wfwd)   # the forward gemm: splits lhs row-wise and leaves its column scales in the scope
+    w = ctx.array(rng.uniform(-1, 1, k * n).astype(np.float32))  # junk: SET
+    b = ctx.array(b0)
+    S.capi.check(ctx.h, L.sl_linear_bwd_params(ctx.h, S.F32, m, k, n, lhs.ptr, og.ptr, w.ptr, b.ptr, -1))
+    if scoped:
+        ctx.gemm_scope_end()
+    assert np.array_equal(w.numpy(), w_ref.numpy())
+    truth = b0.astype(np.float64) + og_h.reshape(m, n).astype(np.float64).sum(0)
+    tol = 4 * m * 2.0 ** -24
+    assert np.max(np.abs(b.numpy() - truth)) <= tol and np.max(np.abs(b_ref.numpy() - truth)) <= tol
+    # NULL bias gradient: weights only
+    w2 = ctx.zeros(k * n)
+    S.capi.check(ctx.h, L.sl_linear_bwd_params(ctx.h, S.F32, m, k, n, lhs.ptr, og.ptr, w2.ptr, None, -1))
+    assert np.array_equal(w2.numpy(), w_ref.numpy())
+    ctx.close()
+
+
+def test_fused_step_large_matches_tape():
+    """the fused step at a size where every big gemm runs the 3xFP16 kernel (bias gradients come from the fused column pass, in a
+    different summation order than the tape's sum_rows): gradients and weights agree to fp32 round-off, losses/accuracy exactly
+    on step 1."""
+    from sliced_b200.host import CUDA, Mlp
+    dims, batch = [2048, 2560, 2304, 10], 4096
+    x, y, labels, W, B = make_problem(dims, batch, 9)
+    # Xavier-sized weights: U(-0.1, 0.1) at this width saturates the softmax (0/0 in the reference's cce_grad)
+    W = [(w * 10 * np.sqrt(6.0 / (dims[i] + dims[i + 1]))).astype(np.float32) for i, w in enumerate(W)]
+    res = []
+    for fused in (False, True):
+        dev = CUDA(0, cached=True)
+        mlp = Mlp(dev, dims, 0)
+        mlp.set_fused(fused)
+        for l in range(len(dims) - 1):
+            mlp.weights(l).write(W[l]); mlp.bias(l).write(B[l])
+        dx, dy, dl = dev.buffer(x).no_grad(), dev.buffer(y).no_grad(), dev.buffer(labels)
+        hist = [mlp.step(dx, dy, dl, batch, 0.1) for _ in range(2)]
+        res.append((hist, mlp.params().read(), mlp.grad_bucket().read()))
+        del mlp, dx, dy, dl
+        dev.close()
+    (h0, p0, g0), (h1, p1, g1) = res
+    assert h0[0] == h1[0]
+    assert np.max(np.abs(g0 - g1)) <= 1e-5 * np.max(np.abs(g0)), np.max(np.abs(g0 - g1))
+    assert np.max(np.abs(p0 - p1)) <= 1e-6 * max(1.0, np.max(np.abs(p0)))
+
+
 def test_graph_replay_equals_eager_sine_net():
     """examples/sine_net.rs `sine_net_lazy2` (:178-233): build the graph once, replay it — CUDA-graph replay of the captured step
     gives bit-identical weights and losses to the eager tape."""

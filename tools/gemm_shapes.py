@@ -24,6 +24,7 @@ def buf(n):
 shapes = [("fwd  NN", 0, 0, 65536, 4096, 4096), ("dA   NT", 0, 1, 65536, 4096, 4096), ("dW   TN", 1, 0, 4096, 4096, 65536),
           ("sq   NT", 0, 1, 8192, 8192, 8192)]
 B = int(os.environ.get("BATCH", "65536"))
+MODE = {"3xf16": S.GEMM_3XF16, "3xtf32": S.GEMM_3XTF32, "tf32": S.GEMM_TF32}[os.environ.get("MODE", "3xf16")]
 for name, ta, tb, m, n, k in shapes:
     if name.startswith(("fwd", "dA")):
         m = B
@@ -36,7 +37,7 @@ for name, ta, tb, m, n, k in shapes:
         for kc in os.environ.get("KCS", "4").split(","):
             os.environ["SLICED_GEMM_CFG"] = cfg
             os.environ["SLICED_GEMM_KC"] = kc
-            fn = lambda: L.sl_gemm_ex(ctx.h, S.F32, ta, tb, m, n, k, a.ptr, b.ptr, c.ptr, 0, S.GEMM_3XTF32)
+            fn = lambda: L.sl_gemm_ex(ctx.h, S.F32, ta, tb, m, n, k, a.ptr, b.ptr, c.ptr, 0, MODE)
             for _ in range(2):
                 assert fn() == 0
             capi.check(ctx.h, L.sl_ctx_profile_begin(ctx.h))
