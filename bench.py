@@ -334,6 +334,29 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     barrier()
 
+    if rank == 0 and args.breakdown:
+        # in-situ per-kernel times (CUDA events around EVERY launch of a few extra steps; not part of any reported number)
+        buf = C.create_string_buffer(1 << 16)
+        capi.check(ctx, lib.sl_ctx_profile_report(ctx, None, 0))     # switch on per-launch timing
+        capi.check(ctx, lib.sl_ctx_profile_begin(ctx))
+        bsteps = 5
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        for _ in range(bsteps):
+            resident_step(False)
+        b1.record(stream)
+        torch.cuda.synchronize()
+        capi.check(ctx, lib.sl_ctx_profile_report(ctx, buf, len(buf)))
+        capi.check(ctx, lib.sl_ctx_profile_end(ctx, None, None, None))
+        wall = b0.elapsed_time(b1) / bsteps
+        rows = [r.rsplit(",", 2) for r in buf.value.decode().strip().splitlines()]
+        tot = sum(float(r[2]) for r in rows) / bsteps
+        with open(args.breakdown, "w") as f:
+            f.write(f"# per-kernel CUDA-event times inside the training step, N={world}, batch {batch}, {args.gemm_mode}; {bsteps} steps averaged\n")
+            f.write(f"# step (events around every launch add gaps): {wall:.3f} ms; sum of kernels: {tot:.3f} ms\n")
+            f.write(f"# {'kernel':60s} launches/step   ms/step   share\n")
+            for name, n, ms in rows:
+                f.write(f"{name[:62]:62s} {int(n) / bsteps:8.1f} {float(ms) / bsteps:10.4f} {100 * float(ms) / bsteps / tot:7.2f}%\n")
     if rank == 0:
         pk = peaks()
         f16 = args.gemm_mode == "3xf16"
@@ -376,6 +399,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
+    ap.add_argument("--breakdown", default=None, help="write an in-situ per-kernel time table of the step to this path")
     ap.add_argument("--gemm-mode", choices=["3xtf32", "tf32", "3xf16"], default="3xf16")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

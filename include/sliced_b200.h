@@ -120,6 +120,9 @@ uint64_t sl_ctx_launch_count(sl_ctx* ctx);
  * launches, their summed device time (ms) and their summed algorithmic flops (2*M*N*K each). */
 int sl_ctx_profile_begin(sl_ctx* ctx);
 int sl_ctx_profile_end(sl_ctx* ctx, uint64_t* n_launches, double* total_ms, double* total_flops);
+/* In-situ per-kernel timing (tools/step_breakdown.py): the first call switches the context to timing EVERY launch between
+ * sl_ctx_profile_begin and _end; called between them it writes "kernel,launches,total_ms" lines (sorted by time) into out. */
+int sl_ctx_profile_report(sl_ctx* ctx, char* out, size_t cap);
 
 /* ref: custos `Alloc<T>::alloc` / `OnDropBuffer` † */
 int sl_malloc(sl_ctx* ctx, size_t bytes, void** out_dptr);

@@ -73,6 +73,7 @@ def _declare(lib):
         "sl_ctx_launch_count": ([_vp], C.c_uint64),
         "sl_ctx_profile_begin": ([_vp], _i),
         "sl_ctx_profile_end": ([_vp, P(C.c_uint64), P(_d), P(_d)], _i),
+        "sl_ctx_profile_report": ([_vp, C.c_char_p, _sz], _i),
         "sl_malloc": ([_vp, _sz, P(_vp)], _i),
         "sl_free": ([_vp, _vp], _i),
         "sl_host_alloc": ([_vp, _sz, P(_vp)], _i),

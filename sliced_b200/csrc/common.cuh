@@ -26,8 +26,9 @@ struct sl_ctx {
     size_t ws2_bytes = 0;
     // optional per-launch event timing of the gemm MMA kernel (sl_ctx_profile_begin / _end)
     bool profiling = false;
-    struct ProfRec { cudaEvent_t a, b; double flops; };
+    struct ProfRec { cudaEvent_t a, b; double flops; const char* name; };
     std::vector<ProfRec> prof;
+    bool profiling_all = false;  // SLICED_PROFILE_ALL / sl_ctx_profile_report: time every kernel launch, not only the MMA kernels
     // operand-plane reuse (sl_gemm_scope_begin / _end): hi/lo TF32 planes of gemm operands kept for later gemms on the same buffer
     struct PlaneEntry { const void* src; size_t elems; float* hi; float* lo; size_t cap_bytes; bool valid; };
     std::vector<PlaneEntry> plane_cache;
@@ -37,6 +38,7 @@ struct sl_ctx {
     struct ColScale { const void* src; size_t rows, cols; float* scale; float* inv; size_t cap; bool valid; };
     std::vector<ColScale> colscale_cache;
     size_t colscale_cursor = 0;
+    std::vector<const void*> cols_split_done;   // buffers already split column-wise in this scope
     // second stream for host->device prefetch (sl_write_prefetch), created lazily
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_done = nullptr, compute_done = nullptr;
@@ -68,7 +70,19 @@ int sl_ws2_reserve(sl_ctx* ctx, size_t bytes, void** out);
 // Launch + count + check.  Every kernel this library runs goes through here (sl_ctx_launch_count).
 #define SL_LAUNCH(ctx, kernel, grid, block, smem, ...)                                               \
     do {                                                                                             \
+        sl_ctx::ProfRec pr__{};                                                                      \
+        const bool prof__ = (ctx)->profiling && (ctx)->profiling_all;                                \
+        if (prof__) {                                                                                \
+            cudaEventCreate(&pr__.a);                                                                \
+            cudaEventCreate(&pr__.b);                                                                \
+            pr__.name = #kernel;                                                                     \
+            cudaEventRecord(pr__.a, (ctx)->stream);                                                  \
+        }                                                                                            \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                             \
+        if (prof__) {                                                                                \
+            cudaEventRecord(pr__.b, (ctx)->stream);                                                  \
+            (ctx)->prof.push_back(pr__);                                                             \
+        }                                                                                            \
         (ctx)->launches++;                                                                           \
         cudaError_t e__ = cudaGetLastError();                                                        \
         if (e__ != cudaSuccess)                                                                      \

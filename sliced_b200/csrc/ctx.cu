@@ -143,20 +143,54 @@ int sl_ctx_profile_begin(sl_ctx* ctx) {
     return SL_OK;
 }
 
+// Per-kernel report of everything launched since sl_ctx_profile_begin (call BEFORE sl_ctx_profile_end): one line
+// "name,launches,total_ms" per kernel, sorted by time.  Enables timing of every launch from the next _begin on.
+int sl_ctx_profile_report(sl_ctx* ctx, char* out, size_t cap) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    ctx->profiling_all = true;
+    if (!out || cap == 0) return SL_OK;
+    out[0] = 0;
+    SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<std::pair<std::string, std::pair<int, double>>> agg;
+    for (auto& r : ctx->prof) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+        const std::string nm = r.name ? r.name : "gemm_mma";
+        bool found = false;
+        for (auto& a : agg)
+            if (a.first == nm) { a.second.first++; a.second.second += t; found = true; break; }
+        if (!found) agg.push_back({nm, {1, (double)t}});
+    }
+    for (size_t i = 0; i < agg.size(); ++i)
+        for (size_t j = i + 1; j < agg.size(); ++j)
+            if (agg[j].second.second > agg[i].second.second) std::swap(agg[i], agg[j]);
+    size_t pos = 0;
+    for (auto& a : agg) {
+        int n = snprintf(out + pos, cap - pos, "%s,%d,%.4f\n", a.first.c_str(), a.second.first, a.second.second);
+        if (n < 0 || (size_t)n >= cap - pos) break;
+        pos += n;
+    }
+    return SL_OK;
+}
+
 int sl_ctx_profile_end(sl_ctx* ctx, uint64_t* n_launches, double* total_ms, double* total_flops) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     ctx->profiling = false;
     SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double ms = 0, fl = 0;
+    uint64_t n_mma = 0;
     for (auto& r : ctx->prof) {
         float t = 0;
         SL_CUDA(ctx, cudaEventElapsedTime(&t, r.a, r.b));
-        ms += t;
-        fl += r.flops;
+        if (r.flops > 0) {   // the MMA kernels (the other records exist only in profiling_all mode)
+            ms += t;
+            fl += r.flops;
+            n_mma++;
+        }
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
-    if (n_launches) *n_launches = ctx->prof.size();
+    if (n_launches) *n_launches = n_mma;
     if (total_ms) *total_ms = ms;
     if (total_flops) *total_flops = fl;
     ctx->prof.clear();

@@ -1020,47 +1020,48 @@ __device__ __forceinline__ void split4_store(const float4& v, float sx, float sy
     *reinterpret_cast<uint2*>(lo) = *reinterpret_cast<const uint2*>(l);
 }
 
-// K-contiguous operand [R x K] (K % 4 == 0): one block per row.  Rows of up to 8192 elements are held in registers between the
-// max pass and the split pass (one HBM read); longer rows are re-read (L2).
-// colmax_partial (optional, register-cached rows only): [gridDim.x][K] running max |x| per column over the rows this block handled —
-// the column scales the same buffer needs when it is later used with the other index contracted (weight-gradient gemm).
-__global__ void __launch_bounds__(256) prep16_rows_kernel(size_t R, size_t K, const float* __restrict__ src, __half* __restrict__ hi,
+// K-contiguous operand [R x K] (K % 4 == 0): one 128-thread block per row, several blocks resident per SM so that one row's
+// load latency hides behind the others' reductions and stores.  VPT float4 per thread hold a row of up to 512 * VPT elements in
+// registers between the max pass and the split pass (one HBM read); VPT = 0: longer rows, re-read (L2).
+// COLMAX: also keep max |x| per column over the rows this block handled -> colmax_partial[gridDim.x][K]: the column scales the same
+// buffer needs when a later gemm contracts over its rows instead (weight-gradient gemm).
+template <int VPT, bool COLMAX>
+__global__ void __launch_bounds__(128) prep16_rows_kernel(size_t R, size_t K, const float* __restrict__ src, __half* __restrict__ hi,
                                                           __half* __restrict__ lo, float* __restrict__ scale_inv, float* __restrict__ colmax_partial) {
-    __shared__ float red[8];
+    constexpr int NV = VPT > 0 ? VPT : 1;
+    __shared__ float red[4];
     __shared__ float bcast;
     const size_t nv = K / 4;
-    const bool cached = nv <= 8 * 256;
-    float4 cm[8];
+    float4 cm[NV];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NV; ++i) cm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (size_t row = blockIdx.x; row < R; row += gridDim.x) {
         const float4* s4 = reinterpret_cast<const float4*>(src + row * K);
-        float4 v[8];
+        float4 v[NV];
         float m = 0.f;
-        if (cached) {
+        if (VPT > 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const size_t idx = threadIdx.x + (size_t)i * 256;
+            for (int i = 0; i < NV; ++i) {
+                const size_t idx = threadIdx.x + (size_t)i * 128;
                 if (idx < nv) {
-                    v[i] = __ldg(s4 + idx);
+                    const Pack<float> p = ld_stream(src + row * K + idx * 4);
+                    v[i] = make_float4(p.v[0], p.v[1], p.v[2], p.v[3]);
                     m = absmax4(m, v[i]);
-                    if (colmax_partial) {
+                    if (COLMAX) {
                         cm[i].x = fmaxf(cm[i].x, fabsf(v[i].x)); cm[i].y = fmaxf(cm[i].y, fabsf(v[i].y));
                         cm[i].z = fmaxf(cm[i].z, fabsf(v[i].z)); cm[i].w = fmaxf(cm[i].w, fabsf(v[i].w));
                     }
                 }
             }
         } else {
-            for (size_t idx = threadIdx.x; idx < nv; idx += 256) m = absmax4(m, __ldg(s4 + idx));
+            for (size_t idx = threadIdx.x; idx < nv; idx += 128) m = absmax4(m, __ldg(s4 + idx));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
         __syncthreads();
         if (threadIdx.x == 0) {
-            float t = red[0];
-#pragma unroll
-            for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w]);
+            const float t = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
             float inv;
             bcast = scale_for_max(t, &inv);
             scale_inv[row] = inv;
@@ -1069,21 +1070,21 @@ __global__ void __launch_bounds__(256) prep16_rows_kernel(size_t R, size_t K, co
         const float sc = bcast;
         __half* h = hi + row * K;
         __half* l = lo + row * K;
-        if (cached) {
+        if (VPT > 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const size_t idx = threadIdx.x + (size_t)i * 256;
+            for (int i = 0; i < NV; ++i) {
+                const size_t idx = threadIdx.x + (size_t)i * 128;
                 if (idx < nv) split4_store(v[i], sc, sc, sc, sc, h + idx * 4, l + idx * 4);
             }
         } else {
-            for (size_t idx = threadIdx.x; idx < nv; idx += 256) split4_store(__ldg(s4 + idx), sc, sc, sc, sc, h + idx * 4, l + idx * 4);
+            for (size_t idx = threadIdx.x; idx < nv; idx += 128) split4_store(__ldg(s4 + idx), sc, sc, sc, sc, h + idx * 4, l + idx * 4);
         }
-        __syncthreads();
+        // (the next iteration's first __syncthreads orders this row's read of `bcast` before the next write)
     }
-    if (colmax_partial && cached) {
+    if (COLMAX && VPT > 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const size_t idx = threadIdx.x + (size_t)i * 256;
+        for (int i = 0; i < NV; ++i) {
+            const size_t idx = threadIdx.x + (size_t)i * 128;
             if (idx < nv) *reinterpret_cast<float4*>(colmax_partial + (size_t)blockIdx.x * K + idx * 4) = cm[i];
         }
     }
@@ -1109,21 +1110,34 @@ __global__ void __launch_bounds__(256) prep16_colmax_kernel(size_t K, size_t R, 
     if (partial_sum) *reinterpret_cast<float4*>(partial_sum + (size_t)blockIdx.y * R + c) = sum;
 }
 // pass 2: fold the slabs -> scale[r], scale_inv[r]
-//         (and the slab sums, in slab order -> sum_acc[r] += total: deterministic)
+//         (and the slab sums, in a fixed order -> sum_acc[r] += total: deterministic)
+// block (32 columns, 8 slab lanes): each thread walks every 8th slab with 4 loads in flight, then the 8 lanes fold in order.
 __global__ void __launch_bounds__(256) prep16_colscale_kernel(size_t R, int slabs, const float* __restrict__ partial, float* __restrict__ scale,
                                                               float* __restrict__ scale_inv, const float* __restrict__ partial_sum,
                                                               float* __restrict__ sum_acc) {
-    const size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (r >= R) return;
-    float m = 0.f;
-    for (int s = 0; s < slabs; ++s) m = fmaxf(m, partial[(size_t)s * R + r]);
-    float inv;
-    scale[r] = scale_for_max(m, &inv);
-    scale_inv[r] = inv;
-    if (partial_sum) {
-        float t = 0.f;
-        for (int s = 0; s < slabs; ++s) t += partial_sum[(size_t)s * R + r];
-        sum_acc[r] += t;
+    __shared__ float sm[8][33], ss[8][33];
+    const size_t r = (size_t)blockIdx.x * 32 + threadIdx.x;
+    float m = 0.f, t = 0.f;
+    if (r < R) {
+#pragma unroll 4
+        for (int s = threadIdx.y; s < slabs; s += 8) {
+            m = fmaxf(m, partial[(size_t)s * R + r]);
+            if (partial_sum) t += partial_sum[(size_t)s * R + r];
+        }
+    }
+    sm[threadIdx.y][threadIdx.x] = m;
+    ss[threadIdx.y][threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.y == 0 && r < R) {
+#pragma unroll
+        for (int y = 1; y < 8; ++y) {
+            m = fmaxf(m, sm[y][threadIdx.x]);
+            t += ss[y][threadIdx.x];
+        }
+        float inv;
+        scale[r] = scale_for_max(m, &inv);
+        scale_inv[r] = inv;
+        if (partial_sum) sum_acc[r] += t;
     }
 }
 // pass 3: element-wise split with the column's scale (planes keep the [K x R] layout)
@@ -1488,19 +1502,30 @@ static int prep16_operand(sl_ctx* ctx, const float* src, size_t mn, size_t k, bo
     const size_t cap = (size_t)ctx->num_sms * 8;
     *inv_out = scale_inv;
     if (k_contiguous) {  // [mn x k]
-        if (ctx->plane_scope && k <= 8192 && mn >= 4 * cap && !colscale_find(ctx, src, mn, k)) {
-            const unsigned grid = (unsigned)cap;
-            void* partial = nullptr;
-            int rc = sl_ws_reserve(ctx, (size_t)grid * k * sizeof(float), &partial);
+        bool seen_cols = false;   // this buffer was already split column-wise in this scope: nobody will ask for its column scales again
+        for (const void* q : ctx->cols_split_done) seen_cols |= (q == (const void*)src);
+        const bool want_colmax = ctx->plane_scope && k <= 8192 && mn >= 4 * cap && !seen_cols && !colscale_find(ctx, src, mn, k);
+        const unsigned grid = (unsigned)(want_colmax ? cap : (mn < cap * 8 ? mn : cap * 8));
+        float* partial = nullptr;
+        sl_ctx::ColScale* e = nullptr;
+        if (want_colmax) {
+            int rc = sl_ws_reserve(ctx, (size_t)grid * k * sizeof(float), (void**)&partial);
             if (rc != SL_OK) return rc;
-            sl_ctx::ColScale* e = nullptr;
             if ((rc = colscale_new(ctx, src, mn, k, &e)) != SL_OK) return rc;
-            SL_LAUNCH(ctx, prep16_rows_kernel, grid, 256, 0, mn, k, src, hi, lo, scale_inv, (float*)partial);
-            SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((k + 255) / 256), 256, 0, k, (int)grid, (const float*)partial, e->scale, e->inv,
-                      (const float*)nullptr, (float*)nullptr);
-            return SL_OK;
         }
-        SL_LAUNCH(ctx, prep16_rows_kernel, (unsigned)(mn < cap * 4 ? mn : cap * 4), 256, 0, mn, k, src, hi, lo, scale_inv, (float*)nullptr);
+#define SL_ROWS(VPTV)                                                                                                                       \
+    do {                                                                                                                                    \
+        if (want_colmax) SL_LAUNCH(ctx, (prep16_rows_kernel<VPTV, true>), grid, 128, 0, mn, k, src, hi, lo, scale_inv, partial);             \
+        else SL_LAUNCH(ctx, (prep16_rows_kernel<VPTV, false>), grid, 128, 0, mn, k, src, hi, lo, scale_inv, (float*)nullptr);               \
+    } while (0)
+        if (k <= 2048) SL_ROWS(4);
+        else if (k <= 4096) SL_ROWS(8);
+        else if (k <= 8192) SL_ROWS(16);
+        else SL_LAUNCH(ctx, (prep16_rows_kernel<0, false>), grid, 128, 0, mn, k, src, hi, lo, scale_inv, (float*)nullptr);
+#undef SL_ROWS
+        if (want_colmax)
+            SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((k + 31) / 32), dim3(32, 8, 1), 0, k, (int)grid, (const float*)partial, e->scale, e->inv,
+                      (const float*)nullptr, (float*)nullptr);
         return SL_OK;
     }
     // [k x mn]: column maxima in two deterministic passes (or from the scope cache), then the element-wise split
@@ -1522,8 +1547,9 @@ static int prep16_operand(sl_ctx* ctx, const float* src, size_t mn, size_t k, bo
         if (rc != SL_OK) return rc;
         float* psum = colsum_acc ? (float*)partial + slabs * mn : nullptr;
         SL_LAUNCH(ctx, prep16_colmax_kernel, dim3((unsigned)col_blocks, (unsigned)slabs, 1), 256, 0, k, mn, rows_per_slab, src, (float*)partial, psum);
-        SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((mn + 255) / 256), 256, 0, mn, (int)slabs, (const float*)partial, scale, scale_inv,
+        SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((mn + 31) / 32), dim3(32, 8, 1), 0, mn, (int)slabs, (const float*)partial, scale, scale_inv,
                   (const float*)psum, colsum_acc);
+        if (ctx->plane_scope) ctx->cols_split_done.push_back(src);
     }
     const size_t total = k * (mn / 4);
     size_t blocks = (total + 255) / 256;
@@ -1736,6 +1762,7 @@ int sl_gemm_scope_begin(sl_ctx* ctx) {
     for (auto& e : ctx->colscale_cache) e.valid = false;
     ctx->plane_cursor = 0;
     ctx->colscale_cursor = 0;
+    ctx->cols_split_done.clear();
     ctx->plane_scope = true;
     return SL_OK;
 }
@@ -1744,6 +1771,7 @@ int sl_gemm_scope_end(sl_ctx* ctx) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     for (auto& e : ctx->plane_cache) e.valid = false;
     for (auto& e : ctx->colscale_cache) e.valid = false;
+    ctx->cols_split_done.clear();
     ctx->plane_scope = false;
     return SL_OK;
 }
