@@ -334,8 +334,9 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     barrier()
 
-    if rank == 0 and args.breakdown:
-        # in-situ per-kernel times (CUDA events around EVERY launch of a few extra steps; not part of any reported number)
+    if args.breakdown:
+        # in-situ per-kernel times (CUDA events around EVERY launch of a few extra steps; not part of any reported number).
+        # EVERY rank runs the extra steps (the step contains the gradient all-reduce); rank 0 writes the table.
         buf = C.create_string_buffer(1 << 16)
         capi.check(ctx, lib.sl_ctx_profile_report(ctx, None, 0))     # switch on per-launch timing
         capi.check(ctx, lib.sl_ctx_profile_begin(ctx))
@@ -351,7 +352,8 @@ def run_ours(args):
         wall = b0.elapsed_time(b1) / bsteps
         rows = [r.rsplit(",", 2) for r in buf.value.decode().strip().splitlines()]
         tot = sum(float(r[2]) for r in rows) / bsteps
-        with open(args.breakdown, "w") as f:
+        barrier()
+        with open(args.breakdown if rank == 0 else os.devnull, "w") as f:
             f.write(f"# per-kernel CUDA-event times inside the training step, N={world}, batch {batch}, {args.gemm_mode}; {bsteps} steps averaged\n")
             f.write(f"# step (events around every launch add gaps): {wall:.3f} ms; sum of kernels: {tot:.3f} ms\n")
             f.write(f"# {'kernel':60s} launches/step   ms/step   share\n")

@@ -2,6 +2,8 @@
 a text summary of the headline metrics per captured launch and, for the dominant gemm kernel, the DRAM traffic per launch that
 bench.py reports as roofline.traffic."""
 import csv
+import os
+import re
 import json
 import subprocess
 import sys
@@ -33,11 +35,13 @@ def main(rep, out_txt, title, traffic_json=None, algorithmic=None):
                 i = hdr.index(k)
                 lines.append(f"{k}: {row[i]} {units[i]}")
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        traffic.append(to_bytes(row[ir], units[ir]) + to_bytes(row[iw], units[iw]))
+        if re.search(os.environ.get("TRAFFIC_KERNEL_RE", "."), row[hdr.index("Kernel Name")]):   # launches that count for the traffic average
+            traffic.append(to_bytes(row[ir], units[ir]) + to_bytes(row[iw], units[iw]))
+            traffic_name = row[hdr.index("Kernel Name")]
         lines.append("")
     open(out_txt, "w").write("\n".join(lines) + "\n")
     if traffic_json:
-        name = rows[2][hdr.index("Kernel Name")]
+        name = traffic_name
         json.dump(dict(kernel=name.split("(")[0].replace("void <unnamed>::", ""), dram_bytes_per_launch=sum(traffic) / len(traffic),
                        launches_captured=len(traffic), algorithmic_bytes_per_launch=algorithmic, source=out_txt), open(traffic_json, "w"), indent=1)
     print(open(out_txt).read())
