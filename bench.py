@@ -230,6 +230,8 @@ def run_ours(args):
         capi.check(ctx, lib.sl_comm_init_rank(ctx, world, rank, idb))
 
     batch = GLOBAL_BATCH // world if args.scaling == "strong" else GLOBAL_BATCH
+    if args.debug_per_gpu_batch:   # diagnosis only (e.g. the per-GPU share of an 8-GPU run on one GPU); the line says so in config
+        batch = args.debug_per_gpu_batch
     global_batch = batch * world
     # synthetic data of the config's shape: this rank's shard (seeded per rank), pinned on the host for the e2e leg
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
@@ -378,7 +380,8 @@ def run_ours(args):
                         step_effective_tflops=step_flops(batch) / (ms_total / args.steps * 1e-3) / 1e12)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step,
                     higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=WORKLOAD, global_batch=global_batch, per_gpu_batch=batch, parallelism=f"dp{world}",
+                    config=dict(workload=WORKLOAD if not args.debug_per_gpu_batch else "DIAGNOSIS RUN (per-GPU batch overridden): " + WORKLOAD,
+                                global_batch=global_batch, per_gpu_batch=batch, parallelism=f"dp{world}",
                                 gemm_mode=args.gemm_mode, fused_epilogues=not args.unfused, l2="inputs (>= 128 MiB per operand at every N) exceed the 126 MB L2; no flush needed"),
                     e2e=dict(value=global_batch / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline,
@@ -401,6 +404,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
+    ap.add_argument("--debug-per-gpu-batch", type=int, default=0, help="diagnosis only: override the per-GPU batch (not the BASELINE workload)")
     ap.add_argument("--breakdown", default=None, help="write an in-situ per-kernel time table of the step to this path")
     ap.add_argument("--gemm-mode", choices=["3xtf32", "tf32", "3xf16"], default="3xf16")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="batch of the bounded CPU-baseline sample")
