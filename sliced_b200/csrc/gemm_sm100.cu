@@ -217,6 +217,7 @@ struct GemmParams {
     const float* col_scale; //   operand scaling) before anything else; both NULL otherwise
     int kc_first;           // 2-CTA kernel: k-blocks of the FIRST TWO chunks of every tile (>= kc_blocks; see the kernel)
     int debug;              // bit 0: skip the final store (timing experiments only, SLICED_GEMM_DEBUG)
+    unsigned long long hint_a, hint_b;   // L2 eviction-priority policy of the A / B operand loads (0 = none)
 };
 
 // shared epilogue arithmetic of both MMA kernels: 4 consecutive columns of one output row
@@ -513,6 +514,15 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtenso
         : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_leader), "r"(c0), "r"(c1)
         : "memory");
 }
+// same with an L2 eviction-priority hint (createpolicy encodings: evict_first for a streamed operand, evict_last for a re-read one)
+__device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar_leader, int32_t c0, int32_t c1,
+                                                     uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        :
+        : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_leader), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -723,19 +733,23 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                     const uint32_t fb = mapa_shared(full_bar(stage), 0);  // the leader's barrier, as a shared::cluster address
                     if (leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
                     // K-major plane: one box {BLOCK_K k, 128 rows}; MN-major plane: one box {32 | 64 mn, BLOCK_K k} per chunk
-                    auto load_plane = [&](uint32_t dst, const CUtensorMap* map, int row0, bool mn) {
+                    auto load_box = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t hint) {
+                        if (hint) tma_load_2d_2sm_hint(dst, map, fb, c0, c1, hint);
+                        else tma_load_2d_2sm(dst, map, fb, c0, c1);
+                    };
+                    auto load_plane = [&](uint32_t dst, const CUtensorMap* map, int row0, bool mn, uint64_t hint) {
                         if (!mn) {
-                            tma_load_2d_2sm(dst, map, fb, kb * BLOCK_K, row0);
+                            load_box(dst, map, kb * BLOCK_K, row0, hint);
                         } else {
 #pragma unroll
-                            for (int g = 0; g < MN_CHUNKS; ++g) tma_load_2d_2sm(dst + g * MN_CHUNK_BYTES, map, fb, row0 + g * MN_CHUNK_ROWS, kb * BLOCK_K);
+                            for (int g = 0; g < MN_CHUNKS; ++g) load_box(dst + g * MN_CHUNK_BYTES, map, row0 + g * MN_CHUNK_ROWS, kb * BLOCK_K, hint);
                         }
                     };
-                    load_plane(sa, &map_a_hi, row_a, A_MN);
-                    load_plane(sb, &map_b_hi, row_b, B_MN);
+                    load_plane(sa, &map_a_hi, row_a, A_MN, p.hint_a);
+                    load_plane(sb, &map_b_hi, row_b, B_MN, p.hint_b);
                     if (TERMS == 3) {
-                        load_plane(sa + Cfg::A_BYTES, &map_a_lo, row_a, A_MN);
-                        load_plane(sb + Cfg::B_BYTES, &map_b_lo, row_b, B_MN);
+                        load_plane(sa + Cfg::A_BYTES, &map_a_lo, row_a, A_MN, p.hint_a);
+                        load_plane(sb + Cfg::B_BYTES, &map_b_lo, row_b, B_MN, p.hint_b);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -1321,6 +1335,20 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
     p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu; p.C2 = c2; p.mask_src = mask_src;
     p.row_scale = row_scale; p.col_scale = col_scale;
     p.debug = env_int("SLICED_GEMM_DEBUG", 0);
+    // L2 residency: when one operand is much smaller than the other (weights vs a batch of activations) and fits in a fraction of
+    // L2, its loads are marked evict_last and the big, streamed operand's loads evict_first, so the stream does not flush it.
+    p.hint_a = p.hint_b = 0;
+    {
+        const int hint_mode = env_int("SLICED_GEMM_L2HINT", 2);   // 0 off | 1 / 2 see below (1 measured harmful: 12 GB, the streamed
+                                                                   // operand is still shared by the 16 tiles of its row band)
+        const double a_bytes = (double)M * K * 4, b_bytes = (double)N * K * 4;   // hi + lo planes
+        constexpr unsigned long long EVICT_FIRST = 0x12F0000000000000ull, EVICT_LAST = 0x14F0000000000000ull;
+        if (hint_mode >= 1) {   // 1: small operand evict_last + streamed operand evict_first; 2: small operand evict_last only
+            const unsigned long long stream = hint_mode == 1 ? EVICT_FIRST : 0ull;
+            if (b_bytes * 4 <= a_bytes && b_bytes <= 80e6) { p.hint_b = EVICT_LAST; p.hint_a = stream; }
+            else if (a_bytes * 4 <= b_bytes && a_bytes <= 80e6) { p.hint_a = EVICT_LAST; p.hint_b = stream; }
+        }
+    }
     p.c_vec_ok = (N % 4 == 0) && sl_aligned16(C) && (!bias || sl_aligned16(bias)) && (!c2 || sl_aligned16(c2)) && (!mask_src || sl_aligned16(mask_src)) &&
                  (!col_scale || sl_aligned16(col_scale));
     const bool three = a_lo != nullptr;
@@ -1335,8 +1363,16 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
     // Tile raster.  Measured on the MLP shapes (tools/raster_sweep.py): narrow groups win — with 2 blocks of the LONG dimension per
     // group the tiles running concurrently span the whole short dimension, so the smaller operand (the weights: 134 MB of hi/lo
     // planes, about one L2) is shared by every CTA pair while the big operand streams through exactly once.
-    p.group = env_int("SLICED_GEMM_GROUP", 2);
-    p.group_along_n = env_int("SLICED_GEMM_GROUP_N", N > M ? 1 : 0);
+    // Re-measured with DRAM counters for the 3xFP16 kernel (tools/raster_traffic.py, profiles/r1_raster_traffic.txt): a long
+    // M with a short N (activations x weights) is best swept in bands of 8 n-blocks (half of the weights stay L2-resident, marked
+    // evict_last, while the activations stream through twice): 6.9 -> 5.6 GB and 4.54 -> 4.33 ms; a deep K (weight gradient) wants
+    // wider groups (8): 15.3 -> 11.9 GB, 4.73 -> 4.53 ms.
+    int def_group = 2, def_along_n = N > M ? 1 : 0;
+    if ((long)K >= 4l * (M > N ? M : N)) { def_group = 8; def_along_n = 0; }
+    else if ((long)M >= 4l * N) { def_group = 8; def_along_n = 1; }
+    else if ((long)N >= 4l * M) { def_group = 8; def_along_n = 0; }
+    p.group = env_int("SLICED_GEMM_GROUP", def_group);
+    p.group_along_n = env_int("SLICED_GEMM_GROUP_N", def_along_n);
     if (p.group < 1) p.group = 1;
     if (cfg == 4) {  // cta_group::2, 256x256 tile per CTA pair
         // Wave quantisation: with T tiles on 74 CTA pairs the last wave is T mod 74 wide (dW of the MLP: 256 tiles = 3.46 waves
