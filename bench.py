@@ -70,7 +70,7 @@ def ncu_traffic():
     try:
         d = json.load(open(p))
         return dict(bytes_per_launch=d["dram_bytes_per_launch"], unit="B", kernel=d["kernel"], algorithmic_bytes_per_launch=d.get("algorithmic_bytes_per_launch"),
-                    source=d.get("source"))
+                    launches_averaged=d.get("launches_captured"), source=d.get("source"))
     except Exception:
         return None
 
@@ -370,7 +370,7 @@ def run_ours(args):
         mult = 1 if args.gemm_mode == "tf32" else 3
         roofline = dict(bound="tensor", kernel="gemm_tf32_2cta_kernel (tcgen05 cta_group::2 %s, TMA, TMEM)" % ("kind::f16" if f16 else "kind::tf32"),
                         achieved=eff, peak=tf32_peak, unit="TFLOP/s",
-                        frac=eff / tf32_peak, traffic=ncu_traffic(),
+                        frac=eff / tf32_peak, traffic=(ncu_traffic() or {}).get("bytes_per_launch"), traffic_detail=ncu_traffic(),
                         peak_src=(f"{pk['src']}: bf16_tflops_sustained (kind::f16 runs at the bf16 rate); kernel timed inside a long step" if f16 else
                                   f"{pk['src']}: bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate); kernel timed inside a long step"),
                         issued_tflops=eff * mult, pipe_util=eff * mult / tf32_peak,
