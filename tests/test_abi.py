@@ -1,5 +1,6 @@
 """CPU-side checks of the drop-in boundary: the library builds for sm_100a, loads without a GPU, exports exactly the
 symbols include/sliced_b200.h declares, and refuses to compute without a device (no CPU fallback)."""
+import os
 import subprocess
 
 import pytest
@@ -42,3 +43,57 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(sliced_b200.SlicedError) as e:
         sliced_b200.Context(0)
     assert e.value.code == capi.SL_ERR_NO_DEVICE
+
+
+def test_rust_sys_crate_matches_header():
+    """bindings/rust/sliced-b200-sys/src/lib.rs is generated from include/sliced_b200.h (tools/gen_rust_sys.py): it must be up to
+    date and declare exactly the header's symbols (rustc is not in the image: this is the check the crate gets)."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    from sliced_b200 import capi
+    lib_rs = open(os.path.join(root, "bindings", "rust", "sliced-b200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (sl_\w+)\(", lib_rs))
+    assert declared == set(capi.declared_symbols())
+
+
+def test_rust_patch_uses_only_declared_symbols():
+    """the authored `cuda.rs` files of bindings/rust/reference-patch call only functions the header declares, with the C prototypes'
+    argument counts"""
+    import re
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    lib_rs = open(os.path.join(root, "bindings", "rust", "sliced-b200-sys", "src", "lib.rs")).read()
+    arity = {m.group(1): (len([a for a in m.group(2).split(",") if a.strip()])) for m in re.finditer(r"pub fn (sl_\w+)\(([^)]*)\)", lib_rs)}
+    patch = os.path.join(root, "bindings", "rust", "reference-patch", "src")
+    used = 0
+    for d, _, files in os.walk(patch):
+        for f in files:
+            if not f.endswith(".rs"):
+                continue
+            txt = open(os.path.join(d, f)).read()
+            txt = re.sub(r"//.*", "", txt)
+            txt = re.sub(r'"(?:[^"\\]|\\.)*"', '""', txt)   # string literals may mention entry points in prose
+            for m in re.finditer(r"\b(sl_[a-z0-9_]+)\s*\(", txt):
+                name = m.group(1)
+                if name in ("sl_ctx",):
+                    continue
+                assert name in arity, f"{f}: {name} is not declared in include/sliced_b200.h"
+                # count top-level commas of the call's argument list
+                i, depth, commas, any_arg = m.end(), 1, 0, False
+                while depth:
+                    c = txt[i]
+                    if c in "([{":
+                        depth += 1
+                    elif c in ")]}":
+                        depth -= 1
+                    elif c == "," and depth == 1:
+                        commas += 1
+                    elif not c.isspace():
+                        any_arg = True
+                    i += 1
+                assert (commas + 1 if any_arg else 0) == arity[name], f"{f}: {name} called with {commas + 1} args, header has {arity[name]}"
+                used += 1
+    assert used >= 20
