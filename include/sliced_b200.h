@@ -237,6 +237,14 @@ int sl_gemm_grad(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const voi
 int sl_linear_bwd_params(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* out_grad, void* w_grad, void* b_grad,
                          int mode);
 
+/* Data-parallel form of sl_linear_bwd_params: the same gradients, each handed to sl_allreduce_sum_async as soon as it is final
+ * (join with sl_comm_wait).  With chunks > 1 (3xFP16 path, k a multiple of 256*chunks) w_grad is produced in `chunks` row blocks by
+ * separate kernel launches over the same operand planes and every block's exchange starts while the next block is being
+ * multiplied — the exchange of the step's last weight gradient no longer waits for the whole gemm.  A no-op exchange on a
+ * context without a communicator (results identical to sl_linear_bwd_params). */
+int sl_linear_bwd_params_exchange(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* out_grad, void* w_grad,
+                                  void* b_grad, int chunks, int mode);
+
 /* Operand-plane reuse scope for the tensor-core gemm.  Every f32 gemm first derives TF32 hi/lo planes from its operands; between
  * begin and end those planes are kept and reused by later gemms that read the SAME buffer (same pointer and size) — e.g. an
  * activation in its forward gemm and again in the weight-gradient gemm of the same training step.  Contract: a buffer that has

@@ -113,6 +113,7 @@ def _declare(lib):
         "sl_gemm_ex": ([_vp, _i, _i, _i, _sz, _sz, _sz, _vp, _vp, _vp, _i, _i], _i),
         "sl_gemm_grad": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _i, _i], _i),
         "sl_linear_bwd_params": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _i], _i),
+        "sl_linear_bwd_params_exchange": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _i, _i], _i),
         "sl_gemm_scope_begin": ([_vp], _i),
         "sl_gemm_scope_end": ([_vp], _i),
         "sl_linear_fwd": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _i], _i),

@@ -1251,6 +1251,8 @@ static int make_map_mn(sl_ctx* ctx, CUtensorMap* map, const void* base, size_t r
     return SL_OK;
 }
 
+static int env_int(const char* name, int dflt);
+
 template <int TERMS, int STAGES, bool A_MN, bool B_MN, int KIND = 0>
 static int launch_cfg_2cta(sl_ctx* ctx, const GemmParams& p, const void* a_hi, const void* a_lo, size_t lda, const void* b_hi,
                            const void* b_lo, size_t ldb) {
@@ -1272,7 +1274,10 @@ static int launch_cfg_2cta(sl_ctx* ctx, const GemmParams& p, const void* a_hi, c
     auto kern = gemm_tf32_2cta_kernel<TERMS, STAGES, A_MN, B_MN, KIND>;
     SL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     const int num_tiles = ((p.M + Cfg::TILE_M - 1) / Cfg::TILE_M) * ((p.N + Cfg::TILE_N - 1) / Cfg::TILE_N);
-    const int max_clusters = ctx->num_sms / 2;
+    // data-parallel runs may leave a few SMs to the communication kernels (SLICED_GEMM_RESERVE_SMS, default 0): the persistent gemm
+    // CTAs own all of an SM's shared memory, so an NCCL kernel cannot co-reside with them
+    const int reserve = ctx->nccl_comm ? env_int("SLICED_GEMM_RESERVE_SMS", 0) : 0;
+    const int max_clusters = (ctx->num_sms - (reserve > 0 && reserve < ctx->num_sms - 2 ? reserve : 0)) / 2;
     const int grid = 2 * (num_tiles < max_clusters ? num_tiles : max_clusters);
     sl_ctx::ProfRec rec{};
     if (ctx->profiling) {
@@ -1593,8 +1598,12 @@ static int prep16_operand(sl_ctx* ctx, const float* src, size_t mn, size_t k, bo
     return SL_OK;
 }
 
+int sl_allreduce_sum_async(sl_ctx* ctx, int dtype, void* buf, size_t n);
+
+// m_chunks > 1 (MN-major A only): the product is computed in m_chunks row blocks of C, one kernel launch each, from the same planes;
+// with exchange_chunks every finished block is handed to sl_allreduce_sum_async so that its exchange overlaps the next block's gemm.
 static int gemm_f16x3(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const float* a, const float* b, float* c, int accumulate,
-                      const Epi& epi, float* b_colsum_acc = nullptr) {
+                      const Epi& epi, float* b_colsum_acc = nullptr, int m_chunks = 1, bool exchange_chunks = false) {
     const bool a_kc = !trans_a, b_kc = trans_b != 0;
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t a_plane = up(m * k * 2), b_plane = up(n * k * 2), sm = up(m * 4), sn = up(n * 4);
@@ -1612,8 +1621,21 @@ static int gemm_f16x3(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n,
     const float *a_inv_use = nullptr, *b_inv_use = nullptr;
     if ((rc = prep16_operand(ctx, a, m, k, a_kc, a_hi, a_lo, a_sc, a_inv, &a_inv_use, nullptr)) != SL_OK) return rc;
     if ((rc = prep16_operand(ctx, b, n, k, b_kc, b_hi, b_lo, b_sc, b_inv, &b_inv_use, b_kc ? nullptr : b_colsum_acc)) != SL_OK) return rc;
-    return sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, a_kc ? k : m, b_hi, b_lo, b_kc ? k : n, c, epi.bias, accumulate, epi.relu, epi.c2,
-                             epi.mask_src, a_kc ? 0 : 1, b_kc ? 0 : 1, 1, a_inv_use, b_inv_use);
+    if (m_chunks > 1 && !a_kc && !epi.any() && m % ((size_t)256 * m_chunks) == 0 && sl_gemm_pick_cfg(ctx, m / m_chunks, n) == 4) {
+        const size_t mc = m / m_chunks;
+        for (int ci = 0; ci < m_chunks; ++ci) {
+            const size_t m0 = (size_t)ci * mc;
+            rc = sl_gemm_tc_planes(ctx, (int)mc, (int)n, (int)k, a_hi + m0, a_lo + m0, m, b_hi, b_lo, b_kc ? k : n, c + m0 * n, nullptr, accumulate, 0,
+                                   nullptr, nullptr, 1, b_kc ? 0 : 1, 1, a_inv_use + m0, b_inv_use);
+            if (rc != SL_OK) return rc;
+            if (exchange_chunks && (rc = sl_allreduce_sum_async(ctx, SL_F32, c + m0 * n, mc * n)) != SL_OK) return rc;
+        }
+        return SL_OK;
+    }
+    rc = sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, a_kc ? k : m, b_hi, b_lo, b_kc ? k : n, c, epi.bias, accumulate, epi.relu, epi.c2,
+                           epi.mask_src, a_kc ? 0 : 1, b_kc ? 0 : 1, 1, a_inv_use, b_inv_use);
+    if (rc == SL_OK && exchange_chunks) rc = sl_allreduce_sum_async(ctx, SL_F32, c, m * n);
+    return rc;
 }
 
 static bool f16x3_eligible(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b) {
@@ -1768,8 +1790,21 @@ int sl_linear_bwd_input_relu(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t 
 
 int sl_add_row_mut_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* rhs_grad, const void* out_grad);
 
+static int linear_bwd_params_impl(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* out_grad, void* w_grad,
+                                  void* b_grad, int mode, int chunks, bool exchange);
+
 int sl_linear_bwd_params(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* out_grad, void* w_grad, void* b_grad,
                          int mode) {
+    return linear_bwd_params_impl(ctx, dtype, m, k, n, lhs, out_grad, w_grad, b_grad, mode, 1, false);
+}
+
+int sl_linear_bwd_params_exchange(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* out_grad, void* w_grad,
+                                  void* b_grad, int chunks, int mode) {
+    return linear_bwd_params_impl(ctx, dtype, m, k, n, lhs, out_grad, w_grad, b_grad, mode, chunks < 1 ? 1 : chunks, true);
+}
+
+static int linear_bwd_params_impl(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* out_grad, void* w_grad,
+                                  void* b_grad, int mode, int chunks, bool exchange) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     if (m == 0 || k == 0 || n == 0) return SL_OK;
     SL_REQUIRE(ctx, lhs && out_grad && w_grad, "NULL argument");
@@ -1783,13 +1818,20 @@ int sl_linear_bwd_params(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, c
             for (auto& e : ctx->plane_cache)
                 if (e.valid && e.src == w_grad) e.valid = false;
         }
-        return gemm_f16x3(ctx, 1, 0, k, n, m, (const float*)lhs, (const float*)out_grad, (float*)w_grad, 0, Epi{}, (float*)b_grad);
+        int rc = gemm_f16x3(ctx, 1, 0, k, n, m, (const float*)lhs, (const float*)out_grad, (float*)w_grad, 0, Epi{}, (float*)b_grad, chunks, exchange);
+        if (rc == SL_OK && exchange) rc = sl_allreduce_sum_async(ctx, dtype, b_grad, n);
+        return rc;
     }
     if (b_grad) {
         int rc = sl_add_row_mut_grad(ctx, dtype, m, n, b_grad, out_grad);
         if (rc != SL_OK) return rc;
     }
-    return gemm_ex_impl(ctx, dtype, 1, 0, k, n, m, lhs, out_grad, w_grad, 0, mode, Epi{});
+    int rc = gemm_ex_impl(ctx, dtype, 1, 0, k, n, m, lhs, out_grad, w_grad, 0, mode, Epi{});
+    if (rc == SL_OK && exchange) {
+        rc = sl_allreduce_sum_async(ctx, dtype, w_grad, k * n);
+        if (rc == SL_OK && b_grad) rc = sl_allreduce_sum_async(ctx, dtype, b_grad, n);
+    }
+    return rc;
 }
 
 int sl_gemm_scope_begin(sl_ctx* ctx) {

@@ -177,12 +177,20 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
     for (size_t li = L; li-- > 0;) {
         const size_t I = dims_[li], O = dims_[li + 1];
         const void* lin = li == 0 ? x->dptr : a_[li - 1]->dptr;
-        // b.grad += colsum(gz) ; W.grad = Tgemm(k,n,m,lhs,og) SET — one entry point so that gz is read once for both
-        d.check(sl_linear_bwd_params(c, SL_F32, batch, I, O, lin, gz_[li]->dptr, d.grad(layers_[li].weights.data)->dptr,
-                                     d.grad(layers_[li].bias.data)->dptr, -1));
+        // b.grad += colsum(gz) ; W.grad = Tgemm(k,n,m,lhs,og) SET — one entry point so that gz is read once for both.
         // data-parallel: this layer's gradients are final -> start their sum all-reduce on the communication stream while the
         // remaining layers' backward gemms keep the tensor cores busy (no-op for a world of one)
-        d.check(sl_allreduce_sum_async(c, SL_F32, (float*)bucket_->dptr + seg_off_[2 * li], seg_off_[2 * li + 2] - seg_off_[2 * li]));
+        static const int dp_chunks = getenv("SLICED_DP_CHUNKS") ? atoi(getenv("SLICED_DP_CHUNKS")) : 1;
+        if (dp_chunks > 1) {
+            // experimental (default off): the weight gradient is produced and exchanged in row blocks, so the exchange of the LAST
+            // layer's gradient — which has no later gemm to hide behind — overlaps its own gemm
+            d.check(sl_linear_bwd_params_exchange(c, SL_F32, batch, I, O, lin, gz_[li]->dptr, d.grad(layers_[li].weights.data)->dptr,
+                                                  d.grad(layers_[li].bias.data)->dptr, dp_chunks, -1));
+        } else {
+            d.check(sl_linear_bwd_params(c, SL_F32, batch, I, O, lin, gz_[li]->dptr, d.grad(layers_[li].weights.data)->dptr,
+                                         d.grad(layers_[li].bias.data)->dptr, -1));
+            d.check(sl_allreduce_sum_async(c, SL_F32, (float*)bucket_->dptr + seg_off_[2 * li], seg_off_[2 * li + 2] - seg_off_[2 * li]));
+        }
         if (li > 0)
             d.check(sl_linear_bwd_input_relu(c, SL_F32, batch, I, O, layers_[li].weights.data->dptr, gz_[li]->dptr, z_[li - 1]->dptr,
                                              gz_[li - 1]->dptr, -1));

@@ -196,6 +196,28 @@ def test_linear_bwd_params_equals_composition(shape, scoped):
     ctx.close()
 
 
+def test_linear_bwd_params_exchange_chunked_is_bit_identical():
+    """sl_linear_bwd_params_exchange: the weight gradient produced in row blocks by separate launches over the same operand planes
+    equals the single-launch result bit for bit (no communicator here: the per-block exchange is a no-op)."""
+    import sliced_b200 as S
+    ctx = S.Context(0)
+    L = ctx.lib
+    m, k, n = 2048, 4096, 4096
+    rng = np.random.default_rng(17)
+    lhs = ctx.array(rng.uniform(-1, 1, m * k).astype(np.float32))
+    og = ctx.array(rng.uniform(-1, 1, m * n).astype(np.float32))
+    w_ref, b_ref = ctx.zeros(k * n), ctx.zeros(n)
+    S.capi.check(ctx.h, L.sl_linear_bwd_params(ctx.h, S.F32, m, k, n, lhs.ptr, og.ptr, w_ref.ptr, b_ref.ptr, -1))
+    for chunks in (1, 2, 4, 3):   # 3 does not divide the row count into 256-row multiples -> single launch
+        w = ctx.array(rng.uniform(-1, 1, k * n).astype(np.float32))
+        b = ctx.zeros(n)
+        S.capi.check(ctx.h, L.sl_linear_bwd_params_exchange(ctx.h, S.F32, m, k, n, lhs.ptr, og.ptr, w.ptr, b.ptr, chunks, -1))
+        S.capi.check(ctx.h, L.sl_comm_wait(ctx.h))
+        assert np.array_equal(w.numpy(), w_ref.numpy()), chunks
+        assert np.array_equal(b.numpy(), b_ref.numpy()), chunks
+    ctx.close()
+
+
 def test_fused_step_large_matches_tape():
     """the fused step at a size where every big gemm runs the 3xFP16 kernel (bias gradients come from the fused column pass, in a
     different summation order than the tape's sum_rows): gradients and weights agree to fp32 round-off, losses/accuracy exactly
