@@ -374,6 +374,8 @@ def run_ours(args):
                         peak_src=(f"{pk['src']}: bf16_tflops_sustained (kind::f16 runs at the bf16 rate); kernel timed inside a long step" if f16 else
                                   f"{pk['src']}: bf16_tflops_sustained/2 (dense TF32 = half the bf16 rate); kernel timed inside a long step"),
                         issued_tflops=eff * mult, pipe_util=eff * mult / tf32_peak,
+                        # an f32 gemm's natural yardstick: the dense TF32 rate (half the measured bf16 rate)
+                        frac_of_tf32_peak=eff / (pk["bf16_sustained"] / 2.0),
                         note=f"achieved = algorithmic 2MNK flops of the {n_l.value} tensor-core gemm launches / their summed CUDA-event time "
                              f"({t_ms.value / max(n_l.value, 1):.3f} ms avg); {args.gemm_mode} issues {mult}x those flops to the tensor pipe",
                         gemm_share_of_step=t_ms.value / ms_total if ms_total > 0 else None,
