@@ -120,7 +120,8 @@ def test_tile_configs(cfg, mode):
 
 
 F16_SHAPES = [(128, 256, 128), (256, 256, 64), (640, 768, 1024), (304, 704, 200), (4096, 512, 96), (1112, 2224, 336), (512, 1024, 40),
-              (264, 8, 72), (8, 264, 4104), (2048, 2048, 2048)]
+              (264, 8, 72), (8, 264, 4104), (2048, 2048, 2048),
+              (256, 512, 16392)]   # rows longer than the register-cached limit of the row-wise split (8192)
 
 
 @pytest.mark.parametrize("shape", F16_SHAPES, ids=lambda s: "x".join(map(str, s)))
