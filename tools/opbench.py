@@ -125,11 +125,12 @@ def run_gemm(B, sizes, reps, out, cfgs=("0",)):
     ctx = B.ctx
     _, bf16, src = peaks()
     tf32_peak = bf16 / 2
-    print(f"{'gemm':28s} {'mode':7s} {'cfg':3s} {'ms':>9s} {'eff TF/s':>9s} {'issued TF/s':>11s} {'pipe util (of ' + src + ' tf32 ' + str(tf32_peak) + ')':>36s}")
+    print(f"{'gemm':28s} {'mode':7s} {'cfg':3s} {'ms':>9s} {'eff TF/s':>9s} {'issued TF/s':>11s} {'pipe util (of ' + src + ' bf16 ' + str(bf16) + ' / tf32 ' + str(tf32_peak) + ')':>36s}")
     for (m, n, k) in sizes:
         a, b = B.buf(m * k), B.buf(k * n)
         c = B.buf(m * n, "zeros")
-        for mode, name, mult in ((S.GEMM_3XTF32, "3xtf32", 3), (S.GEMM_TF32, "tf32", 1)):
+        # pipe util: issued flops against the rate of the pipe the mode runs on (kind::f16 = the bf16 rate, kind::tf32 = half of it)
+        for mode, name, mult, pipe_peak in ((S.GEMM_3XF16, "3xf16", 3, bf16), (S.GEMM_3XTF32, "3xtf32", 3, tf32_peak), (S.GEMM_TF32, "tf32", 1, tf32_peak)):
             for cfg in cfgs:
                 os.environ["SLICED_GEMM_CFG"] = cfg
                 for (ta, tb, tag) in ((0, 0, "NN"), (0, 1, "NT"), (1, 0, "TN")):
@@ -138,9 +139,9 @@ def run_gemm(B, sizes, reps, out, cfgs=("0",)):
                     assert rc == 0, ctx.lib.sl_last_error_string(ctx.h)
                     ms, best = B.time(fn, reps)
                     eff = 2.0 * m * n * k / (ms * 1e-3) / 1e12
-                    print(f"{tag} {m}x{n}x{k:<14d} {name:7s} {cfg:3s} {ms:9.3f} {eff:9.1f} {eff * mult:11.1f} {eff * mult / tf32_peak:36.3f}", flush=True)
+                    print(f"{tag} {m}x{n}x{k:<14d} {name:7s} {cfg:3s} {ms:9.3f} {eff:9.1f} {eff * mult:11.1f} {eff * mult / pipe_peak:36.3f}", flush=True)
                     out.append(dict(kind="gemm", layout=tag, m=m, n=n, k=k, mode=name, cfg=cfg, ms=ms, ms_best=best, eff_tflops=eff,
-                                    issued_tflops=eff * mult, pipe_util=eff * mult / tf32_peak, peak_tf32=tf32_peak, peak_src=src))
+                                    issued_tflops=eff * mult, pipe_util=eff * mult / pipe_peak, pipe_peak=pipe_peak, peak_tf32=tf32_peak, peak_src=src))
         os.environ.pop("SLICED_GEMM_CFG", None)
         B.keep.clear()
         torch.cuda.empty_cache()
