@@ -247,9 +247,11 @@ int sl_linear_bwd_params_exchange(sl_ctx* ctx, int dtype, size_t m, size_t k, si
 
 /* Operand-plane reuse scope for the tensor-core gemm.  Every f32 gemm first derives TF32 hi/lo planes from its operands; between
  * begin and end those planes are kept and reused by later gemms that read the SAME buffer (same pointer and size) — e.g. an
- * activation in its forward gemm and again in the weight-gradient gemm of the same training step.  Contract: a buffer that has
- * been read by a gemm inside the scope is not modified by anything but a gemm of this library until the scope ends (a gemm
- * that overwrites it invalidates its planes).  sl_gemm_grad opens an implicit scope around its two gemms (both read out_grad). */
+ * activation in its forward gemm and again in the weight-gradient gemm of the same training step.  Every entry point of this
+ * library that writes device memory (ops, sl_write, sl_copy, sl_clear, the all-reduce) drops the cached planes / scales of the
+ * buffer it writes, so reuse is always coherent with library calls; only writes from OUTSIDE the library (another stream, another
+ * library) to a buffer read by a gemm earlier in the scope are the caller's responsibility.  sl_gemm_grad opens an implicit scope
+ * around its two gemms (both read out_grad). */
 int sl_gemm_scope_begin(sl_ctx* ctx);
 int sl_gemm_scope_end(sl_ctx* ctx);
 
@@ -322,6 +324,18 @@ int sl_softmax(sl_ctx* ctx, int dtype, size_t samples, size_t features, const vo
 int sl_softmax_grad(sl_ctx* ctx, int dtype, size_t samples, size_t features, void* x_grad, const void* out,
                     const void* out_grad);
 
+/* Fused softmax + categorical cross-entropy, forward and backward, for the tail of examples/nn.rs:190-233 in one kernel:
+ *   probs_out       = softmax(logits)                                             (SET)   ref: src/ops2/softmax/cpu.rs:11-16
+ *   loss_per_sample = -ln(sum_c clip(probs, 1e-7, 1 - 1e-7) * targets)  [samples] (SET)   ref: examples/nn.rs:124-138 (cce)
+ *   logits_grad     = softmax_grad(probs, (-(targets / probs)) / grad_rows)       (SET)   ref: examples/nn.rs:140-152 (cce_grad: the
+ *                     division uses the UNCLIPPED probabilities) + src/ops2/softmax/grad/cpu.rs:14-62
+ *   *correct_dev   += #rows whose first arg-max of probs equals labels[row]  (labels / correct_dev may be NULL)  ref: nn.rs:195-211
+ * features <= 32 runs one thread per row and is bit-identical to the chain sl_softmax, sl_unary(CLIP), sl_binary_ew(MUL),
+ * sl_sum_cols, sl_unary(NEG_LN), sl_binary_ew(DIV), sl_unary(NEG_DIV_SCALAR), sl_softmax_grad, sl_count_correct; wider rows use
+ * fixed-order block reductions (K-scaled tolerance).  f32 / f64. */
+int sl_softmax_cce(sl_ctx* ctx, int dtype, size_t samples, size_t features, const void* logits, const void* targets, const int32_t* labels,
+                   size_t grad_rows, void* probs_out, void* logits_grad, void* loss_per_sample, int32_t* correct_dev);
+
 /* ---------------------------------------------------------------- next-row ops */
 
 /* out[i*n + i] = x[i] (only the diagonal is written).  ref: src/ops2/diagflat/cpu.rs:42-46 */
@@ -351,6 +365,13 @@ int sl_allreduce_sum(sl_ctx* ctx, int dtype, void* buf, size_t n);
  * stream wait for every exchange issued so far (call it before the SGD step reads the gradients). */
 int sl_allreduce_sum_async(sl_ctx* ctx, int dtype, void* buf, size_t n);
 int sl_comm_wait(sl_ctx* ctx);
+/* Finer join: the compute stream waits only for the first n exchanges issued (sl_allreduce_sum_async) since the last sl_comm_wait —
+ * they complete in issue order — so the update of a layer whose gradients have arrived runs while later exchanges are still in
+ * flight.  sl_comm_issued returns how many have been issued since the last sl_comm_wait. */
+int sl_comm_wait_n(sl_ctx* ctx, int n);
+int sl_comm_issued(sl_ctx* ctx);
+/* Ranks of the context's communicator (1 without one). */
+int sl_comm_nranks(sl_ctx* ctx);
 int sl_comm_destroy(sl_ctx* ctx);
 
 #ifdef __cplusplus

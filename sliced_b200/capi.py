@@ -137,6 +137,7 @@ def _declare(lib):
         "sl_transpose": ([_vp, _i, _sz, _sz, _vp, _vp, _i], _i),
         "sl_softmax": ([_vp, _i, _sz, _sz, _vp, _vp], _i),
         "sl_softmax_grad": ([_vp, _i, _sz, _sz, _vp, _vp, _vp], _i),
+        "sl_softmax_cce": ([_vp, _i, _sz, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp], _i),
         "sl_diagflat": ([_vp, _i, _sz, _vp, _vp], _i),
         "sl_diagflat_grad": ([_vp, _i, _sz, _vp, _vp], _i),
         "sl_onehot": ([_vp, _i, _sz, _sz, _vp, _vp], _i),
@@ -147,6 +148,9 @@ def _declare(lib):
         "sl_allreduce_sum": ([_vp, _i, _vp, _sz], _i),
         "sl_allreduce_sum_async": ([_vp, _i, _vp, _sz], _i),
         "sl_comm_wait": ([_vp], _i),
+        "sl_comm_wait_n": ([_vp, _i], _i),
+        "sl_comm_issued": ([_vp], _i),
+        "sl_comm_nranks": ([_vp], _i),
         "sl_comm_destroy": ([_vp], _i),
     }
     for name, (args, res) in sig.items():

@@ -49,9 +49,29 @@ struct sl_ctx {
     cudaStream_t comm_stream = nullptr;  // overlapped exchange (sl_allreduce_sum_async)
     cudaEvent_t comm_ready = nullptr, comm_done = nullptr;
     bool comm_pending = false;
+    std::vector<cudaEvent_t> comm_events;   // one per overlapped exchange issued since the last sl_comm_wait (sl_comm_wait_n)
+    size_t comm_issued = 0;
 };
 
 int sl_set_error(sl_ctx* ctx, int code, const char* fmt, ...);
+
+// Plane-cache coherence (sl_gemm_scope_begin / _end): EVERY entry point of the library that writes device memory reports its output
+// pointers here, so cached operand planes / column scales derived from a buffer die as soon as anything overwrites (part of) it.
+static inline void sl_note_write(sl_ctx* ctx, const void* p) {
+    if (!ctx || !ctx->plane_scope || !p) return;
+    const char* q = (const char*)p;
+    for (auto& e : ctx->plane_cache)
+        if (e.valid && q >= (const char*)e.src && q < (const char*)e.src + e.elems * 4) e.valid = false;
+    for (auto& e : ctx->colscale_cache)
+        if (e.valid && q >= (const char*)e.src && q < (const char*)e.src + e.rows * e.cols * 4) e.valid = false;
+    for (auto& d : ctx->cols_split_done)
+        if (d == p) d = nullptr;
+}
+template <typename... P>
+static inline void sl_note_writes(sl_ctx* ctx, P... ptrs) {
+    const void* a[] = {(const void*)ptrs...};
+    for (const void* p : a) sl_note_write(ctx, p);
+}
 int sl_ws_reserve(sl_ctx* ctx, size_t bytes, void** out);
 int sl_ws2_reserve(sl_ctx* ctx, size_t bytes, void** out);
 

@@ -18,8 +18,20 @@ int sl_set_error(sl_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
+// true while ctx->stream is being captured into a CUDA graph (sl_graph_begin .. _end): nothing may synchronise, allocate or free
+static bool capturing(sl_ctx* ctx) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
+
 static int grow(sl_ctx* ctx, void** p, size_t* cur, size_t bytes, void** out) {
     if (bytes > *cur) {
+        if (capturing(ctx))
+            return sl_set_error(ctx, SL_ERR_INVALID_ARG, "scratch would have to grow (%zu -> %zu bytes) during graph capture: run the sequence once eagerly first", *cur, bytes);
         // grow-only; in-flight kernels using the old block are ordered before the free on this stream
         if (*p) {
             SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -201,6 +213,7 @@ int sl_malloc(sl_ctx* ctx, size_t bytes, void** out_dptr) {
     SL_REQUIRE(ctx, ctx && out_dptr, "NULL argument");
     *out_dptr = nullptr;
     if (bytes == 0) return SL_OK;
+    if (capturing(ctx)) return sl_set_error(ctx, SL_ERR_INVALID_ARG, "sl_malloc during graph capture (the captured sequence must be allocation-free)");
     SL_CUDA(ctx, cudaSetDevice(ctx->device));
     SL_CUDA(ctx, cudaMalloc(out_dptr, bytes));
     return SL_OK;
@@ -209,7 +222,10 @@ int sl_malloc(sl_ctx* ctx, size_t bytes, void** out_dptr) {
 int sl_free(sl_ctx* ctx, void* dptr) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     if (!dptr) return SL_OK;
+    if (capturing(ctx)) return sl_set_error(ctx, SL_ERR_INVALID_ARG, "sl_free during graph capture (the captured sequence must be allocation-free)");
     SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) SL_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));   // the buffer may still be in an overlapped exchange
+    if (ctx->copy_stream) SL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     SL_CUDA(ctx, cudaFree(dptr));
     return SL_OK;
 }
@@ -228,6 +244,7 @@ int sl_host_free(sl_ctx* ctx, void* hptr) {
 
 int sl_write(sl_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, dst_dev);
     if (bytes == 0) return SL_OK;
     SL_REQUIRE(ctx, dst_dev && src_host, "NULL pointer");
     SL_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -245,6 +262,7 @@ static int ensure_copy_stream(sl_ctx* ctx) {
 
 int sl_write_prefetch(sl_ctx* ctx, void* dst_dev, const void* src_host_pinned, size_t bytes) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, dst_dev);
     if (bytes == 0) return SL_OK;
     SL_REQUIRE(ctx, dst_dev && src_host_pinned, "NULL pointer");
     int rc = ensure_copy_stream(ctx);
@@ -281,6 +299,7 @@ int sl_read(sl_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
 
 int sl_copy(sl_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, dst_dev);
     if (bytes == 0) return SL_OK;
     SL_REQUIRE(ctx, dst_dev && src_dev, "NULL pointer");
     SL_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -289,6 +308,7 @@ int sl_copy(sl_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
 
 int sl_clear(sl_ctx* ctx, void* dst_dev, size_t bytes) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, dst_dev);
     if (bytes == 0) return SL_OK;
     SL_REQUIRE(ctx, dst_dev, "NULL pointer");
     SL_CUDA(ctx, cudaMemsetAsync(dst_dev, 0, bytes, ctx->stream));

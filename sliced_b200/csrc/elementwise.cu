@@ -221,6 +221,14 @@ struct AddSubGradBothF {
         o[1] += (OP == SL_SUB ? -T(1) : T(1)) * a[0];
     }
 };
+template <typename T, bool NEGATE>
+struct AddSubGradOneF {
+    __device__ __forceinline__ void apply(const T (&a)[1], T (&o)[1]) const { o[0] += (NEGATE ? -T(1) : T(1)) * a[0]; }
+};
+template <typename T>
+struct AddEwGradOneF {
+    __device__ __forceinline__ void apply(const T (&a)[1], T (&o)[1]) const { o[0] += a[0]; }
+};
 template <typename T>
 struct AddEwGradF {
     __device__ __forceinline__ void apply(const T (&a)[1], T (&o)[2]) const {
@@ -323,6 +331,13 @@ int binary_ew_t(sl_ctx* ctx, int op, const void* lhs, const void* rhs, void* out
 template <typename T>
 int binary_ew_grad_t(sl_ctx* ctx, int op, const void* lhs, const void* rhs, void* lg, void* rg, const void* og, size_t n) {
     if (!lg && !rg) return SL_OK;
+    if (lg && lg == rg) {
+        // x.mul(x), add(x, x): both gradients are the SAME buffer.  The reference's loop does `lg[i] += ..; rg[i] += ..` one after the
+        // other (binary_ew/grad/cpu_stack.rs:54-59), so both contributions land; a two-output kernel would preload the element twice
+        // and lose one.  Two one-sided passes give the reference's per-element order: (g + dl*og) + dr*og.
+        int rc = binary_ew_grad_t<T>(ctx, op, lhs, rhs, lg, nullptr, og, n);
+        return rc != SL_OK ? rc : binary_ew_grad_t<T>(ctx, op, lhs, rhs, nullptr, rg, og, n);
+    }
     if ((op == SL_ADD || op == SL_SUB) && lg && rg) {
         EwPtrs<T, 1, 2> p{{(const T*)og}, {(T*)lg, (T*)rg}};
         if (op == SL_ADD) return ew_launch<T, 1, 2, true>(ctx, p, n, AddSubGradBothF<SL_ADD, T>{});
@@ -331,6 +346,10 @@ int binary_ew_grad_t(sl_ctx* ctx, int op, const void* lhs, const void* rhs, void
     if (lg && rg) {
         EwPtrs<T, 3, 2> p{{(const T*)lhs, (const T*)rhs, (const T*)og}, {(T*)lg, (T*)rg}};
         SL_BINOP_SWITCH(op, OPC, return (ew_launch<T, 3, 2, true>(ctx, p, n, BinaryGradBothF<OPC, T>{})));
+    } else if (op == SL_ADD || op == SL_SUB) {   // one-sided add / sub: the operands are not needed (and may be NULL)
+        EwPtrs<T, 1, 1> p{{(const T*)og}, {(T*)(lg ? lg : rg)}};
+        if (op == SL_SUB && !lg) return ew_launch<T, 1, 1, true>(ctx, p, n, AddSubGradOneF<T, true>{});
+        return ew_launch<T, 1, 1, true>(ctx, p, n, AddSubGradOneF<T, false>{});
     } else if (lg) {
         EwPtrs<T, 3, 1> p{{(const T*)lhs, (const T*)rhs, (const T*)og}, {(T*)lg}};
         SL_BINOP_SWITCH(op, OPC, return (ew_launch<T, 3, 1, true>(ctx, p, n, BinaryGradOneF<OPC, T, true>{})));
@@ -365,6 +384,7 @@ extern "C" {
 
 int sl_binary_ew(sl_ctx* ctx, int dtype, int binop, const void* lhs, const void* rhs, void* out, size_t n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out);
     SL_REQUIRE(ctx, n == 0 || (lhs && rhs && out), "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return binary_ew_t<T>(ctx, binop, lhs, rhs, out, n));
     return SL_OK;
@@ -373,6 +393,7 @@ int sl_binary_ew(sl_ctx* ctx, int dtype, int binop, const void* lhs, const void*
 int sl_binary_ew_grad(sl_ctx* ctx, int dtype, int binop, const void* lhs, const void* rhs, void* lhs_grad, void* rhs_grad,
                       const void* out_grad, size_t n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, lhs_grad, rhs_grad);
     SL_REQUIRE(ctx, n == 0 || out_grad, "NULL out_grad");
     SL_REQUIRE(ctx, n == 0 || binop == SL_ADD || binop == SL_SUB || (lhs && rhs), "NULL operand");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return binary_ew_grad_t<T>(ctx, binop, lhs, rhs, lhs_grad, rhs_grad, out_grad, n));
@@ -381,8 +402,14 @@ int sl_binary_ew_grad(sl_ctx* ctx, int dtype, int binop, const void* lhs, const 
 
 int sl_add_ew_grad(sl_ctx* ctx, int dtype, void* lhs_grad, void* rhs_grad, const void* out_grad, size_t n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, lhs_grad, rhs_grad);
     SL_REQUIRE(ctx, n == 0 || (lhs_grad && rhs_grad && out_grad), "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
+        if (lhs_grad == rhs_grad) {   // add2(x, x): the same buffer takes both `+= og` in turn (grad/cpu_stack.rs:80-88)
+            EwPtrs<T, 1, 1> q{{(const T*)out_grad}, {(T*)lhs_grad}};
+            int rc = ew_launch<T, 1, 1, true>(ctx, q, n, AddEwGradOneF<T>{});
+            return rc != SL_OK ? rc : ew_launch<T, 1, 1, true>(ctx, q, n, AddEwGradOneF<T>{});
+        }
         EwPtrs<T, 1, 2> p{{(const T*)out_grad}, {(T*)lhs_grad, (T*)rhs_grad}};
         return ew_launch<T, 1, 2, true>(ctx, p, n, AddEwGradF<T>{});
     });
@@ -391,6 +418,7 @@ int sl_add_ew_grad(sl_ctx* ctx, int dtype, void* lhs_grad, void* rhs_grad, const
 
 int sl_unary(sl_ctx* ctx, int dtype, int unop, double p0, double p1, const void* x, void* out, size_t n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out);
     SL_REQUIRE(ctx, n == 0 || (x && out), "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return unary_t<T>(ctx, unop, p0, p1, x, out, n));
     return SL_OK;
@@ -399,6 +427,7 @@ int sl_unary(sl_ctx* ctx, int dtype, int unop, double p0, double p1, const void*
 int sl_unary_grad(sl_ctx* ctx, int dtype, int unop, double p0, double p1, const void* x, void* x_grad, const void* out_grad,
                   size_t n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, x_grad);
     SL_REQUIRE(ctx, n == 0 || (x && x_grad && out_grad), "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return unary_grad_t<T>(ctx, unop, p0, p1, x, x_grad, out_grad, n));
     return SL_OK;
@@ -406,6 +435,7 @@ int sl_unary_grad(sl_ctx* ctx, int dtype, int unop, double p0, double p1, const 
 
 int sl_sgd_step(sl_ctx* ctx, int dtype, void* w, const void* g, double lr, size_t n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, w);
     SL_REQUIRE(ctx, n == 0 || (w && g), "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
         EwPtrs<T, 1, 1> p{{(const T*)g}, {(T*)w}};
@@ -416,6 +446,7 @@ int sl_sgd_step(sl_ctx* ctx, int dtype, void* w, const void* g, double lr, size_
 
 int sl_fill(sl_ctx* ctx, int dtype, void* dst_dev, double value, size_t n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, dst_dev);
     SL_REQUIRE(ctx, n == 0 || dst_dev, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
         EwPtrs<T, 0, 1> p{{nullptr}, {(T*)dst_dev}};
@@ -426,6 +457,7 @@ int sl_fill(sl_ctx* ctx, int dtype, void* dst_dev, double value, size_t n) {
 
 int sl_chained_fwd(sl_ctx* ctx, int dtype, const void* x, const void* b, void* out, size_t n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out);
     SL_REQUIRE(ctx, n == 0 || (x && b && out), "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
         EwPtrs<T, 2, 1> p{{(const T*)x, (const T*)b}, {(T*)out}};
@@ -437,6 +469,7 @@ int sl_chained_fwd(sl_ctx* ctx, int dtype, const void* x, const void* b, void* o
 int sl_chained_bwd(sl_ctx* ctx, int dtype, const void* x, const void* b, void* x_grad, void* b_grad, const void* out_grad,
                    size_t n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, x_grad, b_grad);
     SL_REQUIRE(ctx, n == 0 || (x && b && x_grad && b_grad && out_grad), "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
         EwPtrs<T, 3, 2> p{{(const T*)x, (const T*)b, (const T*)out_grad}, {(T*)x_grad, (T*)b_grad}};

@@ -1390,11 +1390,23 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
         const int block_k = kind == 1 ? 64 : 32;
         const int num_kb = (K + block_k - 1) / block_k;
         const int max_splits = env_int("SLICED_GEMM_MAX_SPLITS", 4);
+        // cost model (microseconds): waves x k-blocks per unit at the kernel's measured rate, plus what the split costs in HBM
+        // traffic (sp partial tiles written instead of one, then read back and folded).  At K = 65536 (the MLP's weight gradient on
+        // one GPU) the split wins 0.3 ms; at K = 8192 (the same gemm on 8 GPUs) the fold costs more than the partial last wave.
+        const double rate = kind == 1 ? 470e12 : (three ? 240e12 : 600e12);   // algorithmic flop/s of the whole GPU in this mode
+        const double us_wave_kb = 2.0 * 256 * 256 * block_k / (rate / (double)pairs) * 1e6;
+        auto cost = [&](int sp) {
+            const long units = tiles * sp;
+            const long waves = (units + pairs - 1) / pairs;
+            const int kbs = (num_kb + sp - 1) / sp;
+            const double fold_us = sp > 1 ? 2.0 * sp * (double)M * N * 4.0 / 4.0e12 * 1e6 + 4.0 : 0.0;   // measured: 67 us for 2 x 64 MB partials
+            return (double)waves * kbs * us_wave_kb + fold_us;
+        };
         if (eff(tiles) < 0.92)
             for (int sp = 2; sp <= max_splits; ++sp) {
                 const int kbs = (num_kb + sp - 1) / sp;
                 if (kbs * block_k < 2048 || (long)(sp - 1) * kbs >= num_kb) continue;   // keep every split >= 2048 deep and non-empty
-                if (eff(tiles * sp) > eff(tiles * best) + 0.03) best = sp;
+                if (cost(sp) < 0.97 * cost(best)) best = sp;
             }
         GemmParams q = p;
         float* final_c = C;
@@ -1653,12 +1665,7 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
     SL_REQUIRE(ctx, a && b, "NULL operand");
     if (mode < 0) mode = ctx->gemm_mode;
     // a gemm that overwrites a buffer whose planes are cached makes them stale
-    if (ctx->plane_scope)
-        for (auto& e : ctx->plane_cache)
-            if (e.valid && (e.src == c || e.src == (const void*)epi.c2)) e.valid = false;
-    if (ctx->plane_scope)
-        for (auto& e : ctx->colscale_cache)
-            if (e.valid && (e.src == c || e.src == (const void*)epi.c2)) e.valid = false;
+    sl_note_writes(ctx, c, epi.c2);
     if (dtype != SL_F32 || mode == SL_GEMM_SIMT || !tc_eligible(m, n, k)) {
         if (epi.any() && dtype != SL_F32) return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "fused epilogue is f32 only");
         int rc = 1;
@@ -1812,12 +1819,7 @@ static int linear_bwd_params_impl(sl_ctx* ctx, int dtype, size_t m, size_t k, si
     // the weight-gradient gemm contracts over the batch: out_grad is its MN-major B operand, whose column maxima need one full
     // pass over out_grad anyway — that pass also produces the bias gradient's column sums
     if (b_grad && dtype == SL_F32 && mode == SL_GEMM_3XF16 && tc_eligible(k, n, m) && f16x3_eligible(ctx, 1, 0, k, n, m, lhs, out_grad)) {
-        if (ctx->plane_scope) {
-            for (auto& e : ctx->colscale_cache)
-                if (e.valid && e.src == w_grad) e.valid = false;
-            for (auto& e : ctx->plane_cache)
-                if (e.valid && e.src == w_grad) e.valid = false;
-        }
+        sl_note_writes(ctx, w_grad, b_grad);
         int rc = gemm_f16x3(ctx, 1, 0, k, n, m, (const float*)lhs, (const float*)out_grad, (float*)w_grad, 0, Epi{}, (float*)b_grad, chunks, exchange);
         if (rc == SL_OK && exchange) rc = sl_allreduce_sum_async(ctx, dtype, b_grad, n);
         return rc;

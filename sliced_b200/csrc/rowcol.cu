@@ -798,6 +798,7 @@ extern "C" {
 
 int sl_row_op(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, const void* lhs, const void* rhs, void* out) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, out);
     SL_REQUIRE(ctx, lhs && rhs && out, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return row_op_t<T>(ctx, binop, rows, cols, lhs, rhs, out));
     return SL_OK;
@@ -813,6 +814,7 @@ int sl_add_row_mut(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* lhs, 
 
 int sl_add_row_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* lhs_grad, void* rhs_grad, const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, lhs_grad, rhs_grad);
     SL_REQUIRE(ctx, lhs_grad && rhs_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (colreduce_t<T, 1, 0>(ctx, rows, cols, out_grad, nullptr, lhs_grad, rhs_grad, nullptr, 1)));
     return SL_OK;
@@ -820,6 +822,7 @@ int sl_add_row_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* lhs_
 
 int sl_add_row_mut_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* rhs_grad, const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, rhs_grad);
     SL_REQUIRE(ctx, rhs_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (colreduce_t<T, 0, 0>(ctx, rows, cols, out_grad, nullptr, nullptr, rhs_grad, nullptr, 1)));
     return SL_OK;
@@ -828,6 +831,7 @@ int sl_add_row_mut_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* 
 int sl_row_op_grad(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, const void* lhs, const void* rhs, void* lhs_grad,
                    void* rhs_grad, const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, lhs_grad, rhs_grad);
     SL_REQUIRE(ctx, out_grad != nullptr, "NULL out_grad");
     SL_REQUIRE(ctx, binop == SL_ADD || binop == SL_SUB || binop == SL_MUL, "row_op_grad supports ADD/SUB/MUL");
     SL_REQUIRE(ctx, binop != SL_MUL || (lhs && rhs), "MUL needs lhs and rhs");
@@ -855,6 +859,7 @@ int sl_row_op_grad(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, 
 
 int sl_col_op(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, const void* lhs, const void* rhs, void* out) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, out);
     SL_REQUIRE(ctx, lhs && rhs && out, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return col_op_t<T>(ctx, binop, rows, cols, lhs, rhs, out));
     return SL_OK;
@@ -863,6 +868,7 @@ int sl_col_op(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, const
 int sl_col_op_grad(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, const void* lhs, const void* rhs, void* lhs_grad,
                    void* rhs_grad, const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, lhs_grad, rhs_grad);
     SL_REQUIRE(ctx, lhs && rhs && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
         if (lhs_grad) {
@@ -882,6 +888,7 @@ int sl_col_op_grad(sl_ctx* ctx, int dtype, int binop, size_t rows, size_t cols, 
 
 int sl_sum(sl_ctx* ctx, int dtype, const void* x, size_t n, void* out_dev) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out_dev);
     SL_REQUIRE(ctx, out_dev && (n == 0 || x), "NULL pointer");
     if (n == 0) return sl_clear(ctx, out_dev, sl_dtype_size(dtype));
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (scalar_reduce_t<T, 0>(ctx, x, n, out_dev)));
@@ -889,12 +896,14 @@ int sl_sum(sl_ctx* ctx, int dtype, const void* x, size_t n, void* out_dev) {
 }
 int sl_mean(sl_ctx* ctx, int dtype, const void* x, size_t n, void* out_dev) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out_dev);
     SL_REQUIRE(ctx, out_dev && x && n > 0, "NULL pointer or empty buffer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (scalar_reduce_t<T, 1>(ctx, x, n, out_dev)));
     return SL_OK;
 }
 int sl_max(sl_ctx* ctx, int dtype, const void* x, size_t n, void* out_dev) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out_dev);
     SL_REQUIRE(ctx, out_dev && x && n > 0, "Buffer should contain at least an element.");  // src/ops2/max/cpu.rs:24
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (scalar_reduce_t<T, 2>(ctx, x, n, out_dev)));
     return SL_OK;
@@ -902,6 +911,7 @@ int sl_max(sl_ctx* ctx, int dtype, const void* x, size_t n, void* out_dev) {
 
 int sl_sum_rows(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out);
     if (cols == 0) return SL_OK;
     if (rows == 0) return sl_clear(ctx, out, cols * sl_dtype_size(dtype));
     SL_REQUIRE(ctx, x && out, "NULL pointer");
@@ -910,18 +920,21 @@ int sl_sum_rows(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x,
 }
 int sl_mean_rows(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, out);
     SL_REQUIRE(ctx, x && out, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (colreduce_t<T, 0, 0>(ctx, rows, cols, x, nullptr, nullptr, out, nullptr, 2)));
     return SL_OK;
 }
 int sl_max_rows(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out, int32_t* idx_out) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, out, idx_out);
     SL_REQUIRE(ctx, x && out, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (colreduce_t<T, 3, 0>(ctx, rows, cols, x, nullptr, nullptr, out, idx_out, 3)));
     return SL_OK;
 }
 int sl_sum_cols(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out);
     if (rows == 0) return SL_OK;
     if (cols == 0) return sl_clear(ctx, out, rows * sl_dtype_size(dtype));
     SL_REQUIRE(ctx, x && out, "NULL pointer");
@@ -930,12 +943,14 @@ int sl_sum_cols(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x,
 }
 int sl_mean_cols(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, out);
     SL_REQUIRE(ctx, x && out, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (rowreduce_t<T, 1>(ctx, rows, cols, x, out, nullptr)));
     return SL_OK;
 }
 int sl_max_cols(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out, int32_t* idx_out) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, out, idx_out);
     SL_REQUIRE(ctx, x && out, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (rowreduce_t<T, 2>(ctx, rows, cols, x, out, idx_out)));
     return SL_OK;
@@ -943,12 +958,14 @@ int sl_max_cols(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x,
 
 int sl_sum_rows_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_grad, const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, x_grad);
     SL_REQUIRE(ctx, x_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (bcast_acc_t<T, 0>(ctx, rows, cols, x_grad, out_grad, T(0))));
     return SL_OK;
 }
 int sl_mean_rows_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_grad, const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, x_grad);
     SL_REQUIRE(ctx, x_grad && out_grad, "NULL pointer");
     // factor = T(cols) / T(len), computed in T exactly as src/ops2/mean/grad/cpu.rs:45-47 (integer T -> integer division)
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (bcast_acc_t<T, 1>(ctx, rows, cols, x_grad, out_grad, (T)((T)cols / (T)(rows * cols)))));
@@ -956,12 +973,14 @@ int sl_mean_rows_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_
 }
 int sl_sum_cols_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_grad, const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, x_grad);
     SL_REQUIRE(ctx, x_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (bcast_acc_t<T, 2>(ctx, rows, cols, x_grad, out_grad, T(0))));
     return SL_OK;
 }
 int sl_mean_cols_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_grad, const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, x_grad);
     SL_REQUIRE(ctx, x_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, return (bcast_acc_t<T, 3>(ctx, rows, cols, x_grad, out_grad, (T)cols)));
     return SL_OK;
@@ -970,6 +989,7 @@ int sl_mean_cols_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* x_
 int sl_max_rows_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* out, const void* x, void* x_grad,
                      const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, x_grad);
     SL_REQUIRE(ctx, out && x && x_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
         Geo2D g = geo2d<T>(ctx, rows, cols, vec_ok_cols<T>(cols, {out, x, x_grad, out_grad}));
@@ -982,6 +1002,7 @@ int sl_max_rows_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const voi
 int sl_max_cols_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* out, const void* x, void* x_grad,
                      const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, x_grad);
     SL_REQUIRE(ctx, out && x && x_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
         const unsigned grid = tpr_grid(ctx, rows, cols);
@@ -994,6 +1015,7 @@ int sl_max_cols_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const voi
 
 int sl_max_cols_grad_idx(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const int32_t* idx, void* x_grad, const void* out_grad) {
     SL_COMMON_2D_CHECKS();
+    sl_note_writes(ctx, x_grad);
     SL_REQUIRE(ctx, idx && x_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, {
         size_t blocks = (rows + 255) / 256;

@@ -443,12 +443,175 @@ int softmax_grad_t(sl_ctx* ctx, size_t samples, size_t features, void* xg, const
     return SL_OK;
 }
 
+
+// ---------------------------------------------------------------- fused softmax + categorical cross-entropy
+// examples/nn.rs:190-233 after the last Linear, in ONE pass over the logits:
+//   s      = softmax(z)                                   (softmax/cpu.rs:11-16)
+//   loss_r = -ln( sum_c clip(s, 1e-7, 1 - 1e-7)[r,c] * y[r,c] )            cce,      nn.rs:124-138
+//   g      = (-(y / s)) / rows                                            cce_grad, nn.rs:140-152 (unclipped division)
+//   dz     = softmax_grad(s, g) = s * (g - <s, g>)  (SET)                  softmax/grad/cpu.rs:14-62, closed form
+//   correct += (argmax_c s[r,c] == labels[r])                             nn.rs:195-211
+// The thread-per-row form (features <= 32: the 10-class head) performs exactly the per-element operations of the separate
+// kernels (softmax_thread_kernel, unary CLIP, binary MUL, rowreduce sum, unary NEG_LN, binary DIV, unary NEG_DIV_SCALAR,
+// softmax_grad_thread_kernel, count_correct_kernel) in the same order, so every output is bit-identical to that 9-launch chain.
+__device__ __forceinline__ float m_log(float a) { return logf(a); }
+__device__ __forceinline__ double m_log(double a) { return log(a); }
+
+template <typename T>
+__device__ __forceinline__ T cce_clip(T x, T lo, T hi) {
+    const T m = x > lo ? x : lo;
+    return m < hi ? m : hi;
+}
+
+template <typename T, int MAXF>
+__global__ void __launch_bounds__(256) softmax_cce_thread_kernel(size_t samples, size_t features, const T* __restrict__ z, const T* __restrict__ y,
+                                                                 const int32_t* __restrict__ labels, T rows_div, T clip_lo, T clip_hi,
+                                                                 T* __restrict__ probs, T* __restrict__ dz, T* __restrict__ loss_out,
+                                                                 int32_t* correct) {
+    int local = 0;
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < samples; r += (size_t)gridDim.x * blockDim.x) {
+        const T* zr = z + r * features;
+        const T* yr = y + r * features;
+        T sv[MAXF];
+        T mx = zr[0];
+#pragma unroll
+        for (int c = 1; c < MAXF; ++c)
+            if ((size_t)c < features) mx = zr[c] > mx ? zr[c] : mx;
+        T sum = T(0);
+#pragma unroll
+        for (int c = 0; c < MAXF; ++c)
+            if ((size_t)c < features) {
+                sv[c] = m_exp(zr[c] - mx);
+                sum += sv[c];
+            }
+        T loss_acc = T(0), dot = T(0);
+        T smax = T(0);
+        int smi = 0;
+#pragma unroll
+        for (int c = 0; c < MAXF; ++c)
+            if ((size_t)c < features) {
+                const T sc = sv[c] / sum;
+                sv[c] = sc;
+                probs[r * features + c] = sc;
+                loss_acc += cce_clip(sc, clip_lo, clip_hi) * yr[c];
+                const T g = (-(yr[c] / sc)) / rows_div;
+                dot += sc * g;
+                if (c == 0 || sc > smax) {
+                    smax = sc;
+                    smi = c;
+                }
+            }
+#pragma unroll
+        for (int c = 0; c < MAXF; ++c)
+            if ((size_t)c < features) {
+                const T g = (-(yr[c] / sv[c])) / rows_div;
+                dz[r * features + c] = sv[c] * (g - dot);
+            }
+        loss_out[r] = -m_log(loss_acc);
+        if (labels) local += (labels[r] == smi) ? 1 : 0;
+    }
+    if (correct) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(correct, local);  // integer atomics: order-independent
+    }
+}
+
+// any feature count: one block per row, the row is re-read from L1/L2 between the passes (fixed-order block reductions)
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_cce_block_kernel(size_t samples, size_t features, const T* __restrict__ z, const T* __restrict__ y,
+                                                                const int32_t* __restrict__ labels, T rows_div, T clip_lo, T clip_hi,
+                                                                T* __restrict__ probs, T* __restrict__ dz, T* __restrict__ loss_out, int32_t* correct) {
+    __shared__ T s_buf[32];
+    __shared__ int s_idx[8];
+    for (size_t r = blockIdx.x; r < samples; r += gridDim.x) {
+        const T* zr = z + r * features;
+        const T* yr = y + r * features;
+        T* pr = probs + r * features;
+        T mx = zr[0];
+        for (size_t c = threadIdx.x; c < features; c += blockDim.x) mx = zr[c] > mx ? zr[c] : mx;
+        mx = block_reduce<T, true>(mx, s_buf);
+        T sum = T(0);
+        for (size_t c = threadIdx.x; c < features; c += blockDim.x) {
+            const T e = m_exp(zr[c] - mx);
+            pr[c] = e;
+            sum += e;
+        }
+        sum = block_reduce<T, false>(sum, s_buf);
+        T loss_acc = T(0), dot = T(0);
+        T smax = T(-1);
+        int smi = 0x7fffffff;
+        for (size_t c = threadIdx.x; c < features; c += blockDim.x) {   // every thread re-reads only what it wrote itself
+            const T sc = pr[c] / sum;
+            pr[c] = sc;
+            loss_acc += cce_clip(sc, clip_lo, clip_hi) * yr[c];
+            dot += sc * ((-(yr[c] / sc)) / rows_div);
+            if (sc > smax) {
+                smax = sc;
+                smi = (int)c;
+            }
+        }
+        loss_acc = block_reduce<T, false>(loss_acc, s_buf);
+        dot = block_reduce<T, false>(dot, s_buf);
+        for (size_t c = threadIdx.x; c < features; c += blockDim.x) dz[r * features + c] = pr[c] * (((-(yr[c] / pr[c])) / rows_div) - dot);
+        if (labels && correct) {   // first index attaining the maximum: (value, index) folded lane -> warp -> block in a fixed order
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const T ov = __shfl_xor_sync(0xffffffffu, smax, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, smi, o);
+                if (ov > smax || (ov == smax && oi < smi)) {
+                    smax = ov;
+                    smi = oi;
+                }
+            }
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) {
+                s_buf[threadIdx.x >> 5] = smax;
+                s_idx[threadIdx.x >> 5] = smi;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+                    if (s_buf[k] > smax || (s_buf[k] == smax && s_idx[k] < smi)) {
+                        smax = s_buf[k];
+                        smi = s_idx[k];
+                    }
+                if (labels[r] == smi) atomicAdd(correct, 1);
+            }
+        }
+        if (threadIdx.x == 0) loss_out[r] = -m_log(loss_acc);
+        __syncthreads();
+    }
+}
+
+template <typename T>
+int softmax_cce_t(sl_ctx* ctx, size_t samples, size_t features, const void* z, const void* y, const int32_t* labels, size_t grad_rows, void* probs,
+                  void* dz, void* loss, int32_t* correct) {
+    const size_t cap = (size_t)ctx->num_sms * 8;
+    const T rows_div = (T)(double)grad_rows, lo = (T)1E-7, hi = (T)(1. - 1E-7);   // the scalars as custos casts them (f64 literal -> T)
+#define SL_CCE_THREAD(MAXF)                                                                                                                \
+    SL_LAUNCH(ctx, (softmax_cce_thread_kernel<T, MAXF>), (unsigned)(blocks < cap ? blocks : cap), 256, 0, samples, features, (const T*)z,  \
+              (const T*)y, labels, rows_div, lo, hi, (T*)probs, (T*)dz, (T*)loss, correct)
+    if (features <= 32) {
+        const size_t blocks = (samples + 255) / 256;
+        if (features <= 10) SL_CCE_THREAD(10);
+        else if (features <= 16) SL_CCE_THREAD(16);
+        else SL_CCE_THREAD(32);
+        return SL_OK;
+    }
+#undef SL_CCE_THREAD
+    SL_LAUNCH(ctx, (softmax_cce_block_kernel<T>), (unsigned)(samples < cap ? samples : cap), 256, 0, samples, features, (const T*)z, (const T*)y, labels,
+              rows_div, lo, hi, (T*)probs, (T*)dz, (T*)loss, correct);
+    return SL_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 int sl_softmax(sl_ctx* ctx, int dtype, size_t samples, size_t features, const void* x, void* out) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out);
     if (samples == 0 || features == 0) return SL_OK;
     SL_REQUIRE(ctx, x && out, "NULL pointer");
     SL_DISPATCH_FLOAT(ctx, dtype, T, return softmax_t<T>(ctx, samples, features, x, out));
@@ -457,9 +620,23 @@ int sl_softmax(sl_ctx* ctx, int dtype, size_t samples, size_t features, const vo
 
 int sl_softmax_grad(sl_ctx* ctx, int dtype, size_t samples, size_t features, void* x_grad, const void* out, const void* out_grad) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, x_grad);
     if (samples == 0 || features == 0) return SL_OK;
     SL_REQUIRE(ctx, x_grad && out && out_grad, "NULL pointer");
     SL_DISPATCH_FLOAT(ctx, dtype, T, return softmax_grad_t<T>(ctx, samples, features, x_grad, out, out_grad));
+    return SL_OK;
+}
+
+int sl_softmax_cce(sl_ctx* ctx, int dtype, size_t samples, size_t features, const void* logits, const void* targets, const int32_t* labels,
+                   size_t grad_rows, void* probs_out, void* logits_grad, void* loss_per_sample, int32_t* correct_dev) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, probs_out, logits_grad, loss_per_sample, correct_dev);
+    if (samples == 0 || features == 0) return SL_OK;
+    SL_REQUIRE(ctx, logits && targets && probs_out && logits_grad && loss_per_sample, "NULL pointer");
+    SL_REQUIRE(ctx, grad_rows > 0, "grad_rows == 0");
+    SL_DISPATCH_FLOAT(ctx, dtype, T,
+                      return softmax_cce_t<T>(ctx, samples, features, logits, targets, labels, grad_rows, probs_out, logits_grad, loss_per_sample,
+                                              labels ? correct_dev : nullptr));
     return SL_OK;
 }
 

@@ -149,6 +149,7 @@ extern "C" {
 
 int sl_transpose(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x, void* out, int accumulate) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out);
     if (rows == 0 || cols == 0) return SL_OK;
     SL_REQUIRE(ctx, x && out && x != out, "NULL or aliased pointer");
     const size_t ntiles = ((rows + TT - 1) / TT) * ((cols + TT - 1) / TT);
@@ -170,6 +171,7 @@ int sl_transpose(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* x
 
 int sl_diagflat(sl_ctx* ctx, int dtype, size_t n, const void* x, void* out) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out);
     if (n == 0) return SL_OK;
     SL_REQUIRE(ctx, x && out, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, SL_LAUNCH(ctx, (diagflat_kernel<T>), grid1d(ctx, n), 256, 0, n, (const T*)x, (T*)out));
@@ -178,6 +180,7 @@ int sl_diagflat(sl_ctx* ctx, int dtype, size_t n, const void* x, void* out) {
 
 int sl_diagflat_grad(sl_ctx* ctx, int dtype, size_t n, void* x_grad, const void* out_grad) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, x_grad);
     if (n == 0) return SL_OK;
     SL_REQUIRE(ctx, x_grad && out_grad, "NULL pointer");
     SL_DISPATCH_DTYPE(ctx, dtype, T, SL_LAUNCH(ctx, (diagflat_grad_kernel<T>), grid1d(ctx, n), 256, 0, n, (T*)x_grad, (const T*)out_grad));
@@ -186,6 +189,7 @@ int sl_diagflat_grad(sl_ctx* ctx, int dtype, size_t n, void* x_grad, const void*
 
 int sl_onehot(sl_ctx* ctx, int dtype, size_t n, size_t highest_class, const void* classes, void* out) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, out);
     if (n == 0) return SL_OK;
     SL_REQUIRE(ctx, classes && out && highest_class > 0, "bad argument");
     SL_DISPATCH_DTYPE(ctx, dtype, T,
@@ -195,6 +199,7 @@ int sl_onehot(sl_ctx* ctx, int dtype, size_t n, size_t highest_class, const void
 
 int sl_onehot_grad(sl_ctx* ctx, int dtype, size_t n, size_t highest_class, const void* classes, void* classes_grad, const void* out_grad) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, classes_grad);
     if (n == 0) return SL_OK;
     SL_REQUIRE(ctx, classes && classes_grad && out_grad && highest_class > 0, "bad argument");
     SL_DISPATCH_DTYPE(ctx, dtype, T,
@@ -205,6 +210,7 @@ int sl_onehot_grad(sl_ctx* ctx, int dtype, size_t n, size_t highest_class, const
 
 int sl_count_correct(sl_ctx* ctx, int dtype, size_t rows, size_t cols, const void* preds, const int32_t* labels, int32_t* count_dev) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    sl_note_writes(ctx, count_dev);
     SL_REQUIRE(ctx, count_dev != nullptr, "NULL count");
     int rc = sl_clear(ctx, count_dev, sizeof(int32_t));
     if (rc != SL_OK) return rc;

@@ -39,6 +39,7 @@ def _lib():
             "slh_range_begin": ([_vp], None),
             "slh_zero_grad": ([_vp], _i),
             "slh_tape_len": ([_vp], _i),
+            "slh_n_grads": ([_vp], _i),
             "slh_set_tape_enabled": ([_vp, _i], None),
             "slh_set_gemm_mode": ([_vp, _i], _i),
             "slh_buffer_new": ([_vp, _sz, _i], _vp),
@@ -201,6 +202,10 @@ class CUDA:
 
     def tape_len(self) -> int:
         return _lib().slh_tape_len(self.h)
+
+    def n_grads(self) -> int:
+        """number of live gradient buffers (a buffer's gradient is released with the buffer)"""
+        return _lib().slh_n_grads(self.h)
 
     def set_gemm_mode(self, mode: int):
         _chk(_lib().slh_set_gemm_mode(self.h, mode))

@@ -46,6 +46,7 @@ int slh_device_sync(slh_device* d) { return guard([&]() { ((Device*)d)->sync(); 
 void slh_range_begin(slh_device* d) { ((Device*)d)->range_begin(); }
 int slh_zero_grad(slh_device* d) { return guard([&]() { ((Device*)d)->zero_grad(); return 0; }, -1); }
 int slh_tape_len(slh_device* d) { return (int)((Device*)d)->tape_len(); }
+int slh_n_grads(slh_device* d) { return (int)((Device*)d)->n_grads(); }
 void slh_set_tape_enabled(slh_device* d, int on) { ((Device*)d)->set_tape_enabled(on != 0); }
 int slh_set_gemm_mode(slh_device* d, int mode) { return guard([&]() { ((Device*)d)->set_gemm_mode(mode); return 0; }, -1); }
 
@@ -164,8 +165,10 @@ slh_buffer* slh_mlp_params(slh_mlp* m) { return (slh_buffer*)wrap_handle(((Mlp*)
 int slh_mlp_forward_backward(slh_mlp* m, slh_buffer* x, slh_buffer* y, slh_buffer* labels, size_t batch, size_t grad_rows, int want_metrics,
                              double* loss_sum, long long* correct) {
     return guard([&]() {
-        StepResult r = ((Mlp*)m)->forward_backward(((BufHandle*)x)->b, ((BufHandle*)y)->b, labels ? ((BufHandle*)labels)->b : Buf(), batch,
-                                                   grad_rows, want_metrics != 0);
+        Mlp& mlp = *(Mlp*)m;   // the fused step when set_fused(true) (softmax-cce loss only), else the op-by-op tape
+        const Buf lb = labels ? ((BufHandle*)labels)->b : Buf();
+        StepResult r = mlp.fused_active() ? mlp.forward_backward_fused(((BufHandle*)x)->b, ((BufHandle*)y)->b, lb, batch, grad_rows, want_metrics != 0)
+                                          : mlp.forward_backward(((BufHandle*)x)->b, ((BufHandle*)y)->b, lb, batch, grad_rows, want_metrics != 0);
         if (loss_sum) *loss_sum = r.loss_sum;
         if (correct) *correct = r.correct;
         return 0;

@@ -1,9 +1,15 @@
 // mlp.cpp — examples/nn.rs and examples/sine_net.rs training steps on the device (see mlp.hpp).
 #include "mlp.hpp"
 
+#include <cstdlib>
+
 namespace slh {
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
 
 Mlp::Mlp(Device& dev, const std::vector<size_t>& dims, LossKind loss) : dev_(dev), dims_(dims), loss_(loss) {
     if (dims.size() < 2) throw Error(SL_ERR_INVALID_ARG, "Mlp: need at least one layer");
@@ -53,6 +59,10 @@ StepResult Mlp::step_replay(const Buf& x, const Buf& y, const Buf& labels, size_
         dev_.check(sl_graph_destroy(dev_.ctx(), graph_));
         graph_ = nullptr;
     }
+    // a captured step must be allocation-free: the op-by-op tape only is on a Cached device (same buffers every iteration);
+    // the fused softmax-cce step keeps its own persistent activations
+    if (!dev_.cached() && !(fused_ && loss_ == LOSS_SOFTMAX_CCE))
+        throw Error(SL_ERR_INVALID_ARG, "Mlp::step_replay: needs a Cached device (or the fused step): a captured step may not allocate or free");
     StepResult r = step(x, y, labels, batch, grad_rows, lr, want_metrics);   // this call's step, eagerly (creates every buffer)
     dev_.check(sl_graph_begin(dev_.ctx()));
     try {
@@ -139,9 +149,7 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
             a_.push_back(d.buffer(batch * dims_[l + 1], SL_F32));
             gz_.push_back(d.buffer(batch * dims_[l + 1], SL_F32));
         }
-        loss_tmp_[0] = d.buffer(batch * oc, SL_F32);  // clip(out) * y
         loss_tmp_[1] = d.buffer(batch, SL_F32);       // per-sample loss
-        loss_tmp_[2] = d.buffer(batch * oc, SL_F32);  // cce_grad
         fused_batch_ = batch;
     }
     // parameter gradients accumulate (bias: += column sums) -> zero the bucket; activation gradients are all SET
@@ -149,7 +157,11 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
     d.check(sl_clear(c, metrics_dev_, 16));
     // every activation / weight / gz buffer is read by two gemms of this step (forward + a gradient gemm): split each into its
     // TF32 planes once.  Nothing but gemms writes those buffers between here and the end of the backward pass.
-    d.check(sl_gemm_scope_begin(c));
+    struct GemmScope {   // closes the scope on every exit path: a throwing check() must not leave stale planes valid for later calls
+        sl_ctx* c;
+        explicit GemmScope(sl_ctx* ctx) : c(ctx) { sl_gemm_scope_begin(c); }
+        ~GemmScope() { sl_gemm_scope_end(c); }
+    } gemm_scope(c);
 
     // ---- forward: Linear + relu fused; the 10-class head goes through the skinny kernel + add_row_mut + softmax
     const void* in = x->dptr;
@@ -160,44 +172,76 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
         in = a_[l]->dptr;
     }
     Buf out = a_[L - 1];
-    d.check(sl_softmax(c, SL_F32, batch, oc, z_[L - 1]->dptr, out->dptr));
-    if (labels) d.check(sl_count_correct(c, SL_F32, batch, oc, out->dptr, (const int32_t*)labels->dptr, (int32_t*)metrics_dev_ + 1));
-    // cce / cce_grad exactly as nn.rs:124-152 (tiny: batch x 10)
-    const size_t on = batch * oc;
-    d.check(sl_unary(c, SL_F32, SL_UN_CLIP, 1E-7, 1. - 1E-7, out->dptr, loss_tmp_[0]->dptr, on));
-    d.check(sl_binary_ew(c, SL_F32, SL_MUL, loss_tmp_[0]->dptr, y->dptr, loss_tmp_[0]->dptr, on));
-    d.check(sl_sum_cols(c, SL_F32, batch, oc, loss_tmp_[0]->dptr, loss_tmp_[1]->dptr));
-    d.check(sl_unary(c, SL_F32, SL_UN_NEG_LN, 0, 0, loss_tmp_[1]->dptr, loss_tmp_[1]->dptr, batch));
-    d.check(sl_sum(c, SL_F32, loss_tmp_[1]->dptr, batch, metrics_dev_));
-    d.check(sl_binary_ew(c, SL_F32, SL_DIV, y->dptr, out->dptr, loss_tmp_[2]->dptr, on));
-    d.check(sl_unary(c, SL_F32, SL_UN_NEG_DIV_SCALAR, (double)grad_rows, 0, loss_tmp_[2]->dptr, loss_tmp_[2]->dptr, on));
+    // softmax -> accuracy -> cce -> cce_grad -> softmax_grad (nn.rs:190-233: nine launches over batch x 10 on the tape path) as ONE
+    // kernel, bit-identical to that chain (tests/test_gpu_parity.py::test_softmax_cce_fused_equals_chain); + the loss sum
+    d.check(sl_softmax_cce(c, SL_F32, batch, oc, z_[L - 1]->dptr, y->dptr, labels ? (const int32_t*)labels->dptr : nullptr, grad_rows, out->dptr,
+                           gz_[L - 1]->dptr, loss_tmp_[1]->dptr, (int32_t*)metrics_dev_ + 1));
+    d.check(sl_sum(c, SL_F32, loss_tmp_[1]->dptr, batch, metrics_dev_));   // device.mean(&loss) * batch (nn.rs:224)
 
     // ---- backward: the tape of nn.rs in reverse, with gemm_grad(lhs) + relu grad fused
-    d.check(sl_softmax_grad(c, SL_F32, batch, oc, gz_[L - 1]->dptr, out->dptr, loss_tmp_[2]->dptr));       // SET
-    for (size_t li = L; li-- > 0;) {
+    // Data-parallel schedule knobs (read per call, so a sweep can change them at run time; all bit-identical in their results):
+    //   SLICED_DP_CHUNKS   the step's LAST weight-gradient gemm is produced in this many row blocks, each handed to the exchange as it
+    //                      completes: the one exchange with no later gemm to hide behind shrinks to its last block.  Default 4 with a
+    //                      communicator, 1 without.  SLICED_DP_CHUNKS_ALL=1 chunks every layer's weight gradient.
+    //   SLICED_DP_ORDER    0: per layer dW then dX (tape order); 1: the dX chain first, then the weight gradients from the input layer
+    //                      up (the exchanges of the early ones hide behind the later gemms)
+    const bool dp = sl_comm_nranks(c) > 1;
+    const int dp_chunks = env_int("SLICED_DP_CHUNKS", dp ? 4 : 1);
+    const bool chunk_all = env_int("SLICED_DP_CHUNKS_ALL", 0) != 0;
+    const int order = env_int("SLICED_DP_ORDER", 0);
+    layer_exchanges_.assign(L, 0);
+    auto params_grad = [&](size_t li, bool last) {
         const size_t I = dims_[li], O = dims_[li + 1];
         const void* lin = li == 0 ? x->dptr : a_[li - 1]->dptr;
-        // b.grad += colsum(gz) ; W.grad = Tgemm(k,n,m,lhs,og) SET — one entry point so that gz is read once for both.
-        // data-parallel: this layer's gradients are final -> start their sum all-reduce on the communication stream while the
-        // remaining layers' backward gemms keep the tensor cores busy (no-op for a world of one)
-        static const int dp_chunks = getenv("SLICED_DP_CHUNKS") ? atoi(getenv("SLICED_DP_CHUNKS")) : 1;
-        if (dp_chunks > 1) {
-            // experimental (default off): the weight gradient is produced and exchanged in row blocks, so the exchange of the LAST
-            // layer's gradient — which has no later gemm to hide behind — overlaps its own gemm
+        // b.grad += colsum(gz) ; W.grad = Tgemm(k,n,m,lhs,og) SET — one entry point so that gz is read once for both.  This layer's
+        // gradients are then final -> their sum all-reduce starts on the communication stream while the remaining backward gemms keep
+        // the tensor cores busy (no-op for a world of one)
+        const int chunks = (dp_chunks > 1 && (last || chunk_all)) ? dp_chunks : 1;
+        if (chunks > 1) {
             d.check(sl_linear_bwd_params_exchange(c, SL_F32, batch, I, O, lin, gz_[li]->dptr, d.grad(layers_[li].weights.data)->dptr,
-                                                  d.grad(layers_[li].bias.data)->dptr, dp_chunks, -1));
-        } else {
+                                                  d.grad(layers_[li].bias.data)->dptr, chunks, -1));
+        } else {   // one exchange for the layer's whole [W | b] segment of the bucket
             d.check(sl_linear_bwd_params(c, SL_F32, batch, I, O, lin, gz_[li]->dptr, d.grad(layers_[li].weights.data)->dptr,
                                          d.grad(layers_[li].bias.data)->dptr, -1));
             d.check(sl_allreduce_sum_async(c, SL_F32, (float*)bucket_->dptr + seg_off_[2 * li], seg_off_[2 * li + 2] - seg_off_[2 * li]));
         }
-        if (li > 0)
-            d.check(sl_linear_bwd_input_relu(c, SL_F32, batch, I, O, layers_[li].weights.data->dptr, gz_[li]->dptr, z_[li - 1]->dptr,
-                                             gz_[li - 1]->dptr, -1));
+        layer_exchanges_[li] = sl_comm_issued(c);
+        sgd_order_.push_back(li);
+    };
+    auto input_grad = [&](size_t li) {
+        d.check(sl_linear_bwd_input_relu(c, SL_F32, batch, dims_[li], dims_[li + 1], layers_[li].weights.data->dptr, gz_[li]->dptr, z_[li - 1]->dptr,
+                                         gz_[li - 1]->dptr, -1));
+    };
+    sgd_order_.clear();
+    if (order == 1) {
+        for (size_t li = L; li-- > 1;) input_grad(li);
+        for (size_t li = 0; li < L; ++li) params_grad(li, li + 1 == L || (li + 2 == L && dims_.back() <= 16));
+    } else {
+        for (size_t li = L; li-- > 0;) {
+            params_grad(li, li == 0);
+            if (li > 0) input_grad(li);
+        }
     }
-    d.check(sl_gemm_scope_end(c));
     exchanged_ = true;
     return read_metrics(want_metrics);
+}
+
+// Join of the per-layer exchanges and the SGD step, layer by layer in the order the exchanges were issued: the update of a layer
+// whose summed gradients have arrived overlaps the exchanges still in flight (element-wise: identical to one flat sgd()).
+void Mlp::exchange_and_sgd(double lr) {
+    sl_ctx* c = dev_.ctx();
+    if (!exchanged_ || sl_comm_nranks(c) <= 1 || !env_int("SLICED_DP_LAYER_SGD", 1)) {
+        allreduce_grads();
+        sgd(lr);
+        return;
+    }
+    for (size_t li : sgd_order_) {
+        dev_.check(sl_comm_wait_n(c, layer_exchanges_[li]));
+        const size_t off = seg_off_[2 * li], n = seg_off_[2 * li + 2] - off;
+        dev_.check(sl_sgd_step(c, SL_F32, (float*)params_->dptr + off, (float*)bucket_->dptr + off, lr, n));
+    }
+    dev_.check(sl_comm_wait(c));
+    exchanged_ = false;
 }
 
 void Mlp::allreduce_grads() {

@@ -61,13 +61,14 @@ class Mlp {
     StepResult forward_backward_fused(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics);
     void set_fused(bool on) { fused_ = on; }
     bool fused() const { return fused_; }
+    bool fused_active() const { return fused_ && loss_ == LOSS_SOFTMAX_CCE; }
     void allreduce_grads();          // sl_allreduce_sum over the bucket (no-op for a world of one)
     void sgd(double lr);             // SGD::step on every Linear (nn.rs:235-237)
+    void exchange_and_sgd(double lr);  // both, with the update of each layer issued as soon as its exchange has completed
     StepResult step(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, double lr, bool want_metrics) {
         StepResult r = (fused_ && loss_ == LOSS_SOFTMAX_CCE) ? forward_backward_fused(x, y, labels, batch, grad_rows, want_metrics)
                                                                 : forward_backward(x, y, labels, batch, grad_rows, want_metrics);
-        allreduce_grads();
-        sgd(lr);
+        exchange_and_sgd(lr);
         return r;
     }
     // The same step recorded once as a CUDA graph and replayed (custos `Lazy` + `run()`, examples/sine_net.rs:178-233): for the
@@ -90,6 +91,8 @@ class Mlp {
     void* graph_ = nullptr;           // captured step (step_replay)
     struct GraphKey { const void *x, *y, *l; size_t batch, rows; double lr; bool fused; } gkey_{};
     std::vector<size_t> seg_off_;
+    std::vector<int> layer_exchanges_;   // fused backward: number of exchanges issued up to and including layer l's
+    std::vector<size_t> sgd_order_;      // layers in the order their exchanges were issued
     // persistent activations / activation gradients of the fused step (sized for the last batch seen)
     size_t fused_batch_ = 0;
     std::vector<Buf> z_, a_, gz_;

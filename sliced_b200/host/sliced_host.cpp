@@ -8,6 +8,7 @@
 namespace slh {
 
 BufferImpl::~BufferImpl() {
+    if (dev) dev->drop_grad(id);   // custos drops a buffer's gradient with the buffer (OnDropBuffer †)
     if (owns && dptr && dev && dev->ctx()) sl_free(dev->ctx(), dptr);
 }
 
@@ -17,7 +18,16 @@ Device::Device(int device_index, bool cached, void* cuda_stream, bool borrow_str
     check(sl_malloc(ctx_, 16, &scalar_dev_));
 }
 
+void Device::drop_grad(uint64_t id) {
+    if (tearing_down_) return;
+    auto it = grads_.find(id);
+    if (it == grads_.end()) return;
+    Buf g = std::move(it->second);   // destroyed after the erase: its own destructor re-enters drop_grad with another id
+    grads_.erase(it);
+}
+
 Device::~Device() {
+    tearing_down_ = true;
     tape_.clear();
     grads_.clear();
     cache_.clear();

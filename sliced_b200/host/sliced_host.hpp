@@ -71,6 +71,9 @@ class Device {
     // ---- custos Autograd †: tape + gradients
     Buf grad(const Buf& b);                                         // Buffer::grad / grad_mut: lazily zero-allocated
     bool has_grad(const Buf& b) const { return grads_.count(b->id) != 0; }
+    size_t n_grads() const { return grads_.size(); }
+    void drop_grad(uint64_t id);                                    // OnDropBuffer †: a buffer's gradient dies with the buffer
+    bool cached() const { return cached_; }
     void bind_grad(const Buf& b, const Buf& g) { grads_[b->id] = g; }  // place b's gradient in caller-owned memory (DP bucket)
     void zero_grad();                                               // gradients_mut().zero_grad() (examples/nn.rs:186-188)
     void backward(const Buf& out);                                  // seeds ones, runs the tape in reverse, clears it
@@ -128,6 +131,7 @@ class Device {
     std::vector<Buf> cache_;
     size_t cursor_ = 0;
     void* scalar_dev_ = nullptr;
+    bool tearing_down_ = false;
 };
 
 // sliced L4: src/matrix.rs:21-25 — (Buffer, rows, cols)

@@ -320,6 +320,15 @@ class Context:
     def softmax_grad(self, samples, features, x_grad, out, out_grad):
         self._c(self.lib.sl_softmax_grad(self.h, out.code, samples, features, x_grad.ptr, out.ptr, out_grad.ptr))
 
+    def softmax_cce(self, samples, features, logits, targets, labels=None, grad_rows=None):
+        """fused softmax + cce + cce_grad + softmax_grad (+ accuracy): returns (probs, logits_grad, loss_per_sample, correct)"""
+        probs, dz = self.empty(logits.size, logits.dtype), self.empty(logits.size, logits.dtype)
+        loss = self.empty(samples, logits.dtype)
+        cnt = self.zeros(1, np.int32)
+        self._c(self.lib.sl_softmax_cce(self.h, logits.code, samples, features, logits.ptr, targets.ptr, self._p(labels), grad_rows or samples,
+                                        probs.ptr, dz.ptr, loss.ptr, cnt.ptr))
+        return probs, dz, loss, int(cnt.numpy()[0])
+
     def diagflat(self, x):
         out = self.zeros(x.size * x.size, x.dtype)
         self._c(self.lib.sl_diagflat(self.h, x.code, x.size, x.ptr, out.ptr))

@@ -354,3 +354,119 @@ def test_skinny_shapes(case, monkeypatch):
     exact = run(ctx, ta, tb, m, n, k, a, b, S.GEMM_SIMT)          # SIMT mode stays bit-identical to the oracle
     assert np.array_equal(exact, O.gemm_ex(ta, tb, m, n, k, a, b))
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ the shapes the numbers are quoted on
+def _rand32(rng, n, lo=-1.0, hi=1.0):
+    return (rng.random(n, dtype=np.float32) * np.float32(hi - lo) + np.float32(lo)).astype(np.float32)
+
+
+def _sample_idx(rng, m, n, count=40):
+    rows, cols = rng.integers(0, m, count), rng.integers(0, n, count)
+    rows[:6] = [0, m - 1, 127, 128, 255, min(256, m - 1)]
+    cols[:6] = [0, n - 1, 255, min(256, n - 1), 127, 128]
+    return rows, cols
+
+
+def _check_sampled(got, A64, B64, k, rows, cols, extra=None, what=""):
+    """got[rows x cols] against fp64 dot products, 4 K 2^-24 and <= 16x the error of the oracle's own sequential fp32 sgemm on the
+    same sampled entries (A64: [len(rows) x k], B64: [k x len(cols)] as float64 views of the fp32 operands)"""
+    t = A64 @ B64
+    if extra is not None:
+        t = t + extra
+    err = np.max(np.abs(got.astype(np.float64) - t))
+    a32, b32 = np.ascontiguousarray(A64.astype(np.float32)).ravel(), np.ascontiguousarray(B64.astype(np.float32)).ravel()
+    ref = O.gemm_ex(0, 0, len(rows), len(cols), k, a32, b32).reshape(len(rows), len(cols)).astype(np.float64)
+    ref_err = np.max(np.abs(ref - A64 @ B64))
+    assert err <= 4 * k * 2.0 ** -24, f"{what}: err {err} > 4K eps (oracle sgemm err {ref_err})"
+    assert err <= 16 * ref_err + 2.0 ** -22, f"{what}: err {err} vs oracle sgemm err {ref_err}"
+    return err, ref_err
+
+
+MODES = {"3xf16": 3, "3xtf32": 0, "tf32": 1}
+
+
+@pytest.mark.parametrize("mode", ["3xf16", "3xtf32"])
+def test_headline_mlp_shapes_sampled(mode, monkeypatch):
+    """BASELINE configs[4] (nn.rs MLP 4096-4096-4096-10, batch 65536): the three tensor-core products of one layer exactly as the
+    fused step issues them — forward 65536x4096x4096 NN with bias + relu outputs, input gradient NT with the relu mask, weight
+    gradient 4096x4096x65536 TN (K = 65536: the split-K path) with the fused bias gradient — sampled against fp64.
+    3xf16 runs STRICT (no silent 3xTF32 substitution)."""
+    import sliced_b200 as S
+    monkeypatch.delenv("SLICED_GEMM_TC_FORCE", raising=False)   # default dispatch: this is what the benchmark runs
+    if mode == "3xf16":
+        monkeypatch.setenv("SLICED_GEMM_F16_STRICT", "1")
+    ctx = S.Context(0)
+    L, md = ctx.lib, MODES[mode]
+    batch, d = 65536, 4096
+    rng = np.random.default_rng(65536)
+    x, w, bias = _rand32(rng, batch * d, 0, 1), _rand32(rng, d * d, -0.03, 0.03), _rand32(rng, d)
+    dx, dw, db = ctx.array(x), ctx.array(w), ctx.array(bias)
+    X, W = x.reshape(batch, d), w.reshape(d, d)
+    rows, cols = _sample_idx(rng, batch, d)
+    # ---- forward: z = x W + b, a = relu(z)
+    z, a = ctx.empty(batch * d), ctx.empty(batch * d)
+    S.capi.check(ctx.h, L.sl_linear_fwd(ctx.h, S.F32, batch, d, d, dx.ptr, dw.ptr, db.ptr, z.ptr, a.ptr, md))
+    zh = z.numpy().reshape(batch, d)
+    _check_sampled(zh[np.ix_(rows, cols)], X[rows].astype(np.float64), W[:, cols].astype(np.float64), d, rows, cols,
+                   extra=bias[cols].astype(np.float64)[None, :], what=f"fwd {mode}")
+    ah = a.numpy().reshape(batch, d)
+    assert np.array_equal(ah[rows], np.where(zh[rows] >= 0, zh[rows], np.float32(0) * zh[rows]))
+    del ah
+    # ---- input gradient: gx = (z >= 0) * (g W^T)
+    g = _rand32(rng, batch * d)
+    dg = ctx.array(g)
+    G = g.reshape(batch, d)
+    gx = ctx.empty(batch * d)
+    S.capi.check(ctx.h, L.sl_linear_bwd_input_relu(ctx.h, S.F32, batch, d, d, dw.ptr, dg.ptr, z.ptr, gx.ptr, md))
+    gxh = gx.numpy().reshape(batch, d)
+    mask = (zh[np.ix_(rows, cols)] >= 0).astype(np.float64)
+    got = gxh[np.ix_(rows, cols)]
+    assert np.all(got[mask == 0] == 0)
+    t = G[rows].astype(np.float64) @ W[cols].astype(np.float64).T
+    err = np.max(np.abs(got - mask * t))
+    assert err <= 4 * d * 2.0 ** -24 * 0.03 * 4, f"dX {mode}: {err}"
+    del gxh, gx
+    # ---- weight + bias gradient: dW = x^T g (K = batch), db += colsum(g)
+    wg, bg = ctx.empty(d * d), ctx.zeros(d)
+    S.capi.check(ctx.h, L.sl_linear_bwd_params(ctx.h, S.F32, batch, d, d, dx.ptr, dg.ptr, wg.ptr, bg.ptr, md))
+    wgh = wg.numpy().reshape(d, d)
+    r2, c2 = _sample_idx(rng, d, d)
+    _check_sampled(wgh[np.ix_(r2, c2)], X[:, r2].T.astype(np.float64), G[:, c2].astype(np.float64), batch, r2, c2, what=f"dW {mode}")
+    bsum = G.astype(np.float64).sum(0)
+    assert np.max(np.abs(bg.numpy() - bsum)) <= 4 * batch * 2.0 ** -24
+    # the plain Tgemm entry point gives the same weights bit for bit
+    wg2 = ctx.gemm_tn(d, d, batch, dx, dg, mode=md)
+    assert np.array_equal(wg2.numpy().reshape(d, d)[r2], wgh[r2])
+    ctx.close()
+
+
+@pytest.mark.parametrize("size", [4096, 8192, 16384])
+@pytest.mark.parametrize("mode", ["3xf16", "3xtf32", "tf32"])
+def test_cube_sweep_sizes_sampled(size, mode, monkeypatch):
+    """BASELINE configs[2] (gemm sweep M=N=K up to 16384): gemm, gemmT and Tgemm at the large sizes in all three modes, sampled
+    against fp64 (4 K 2^-24 and <= 16x the oracle sgemm's error; TF32 fast mode: 8 sqrt(K) 2^-11)."""
+    import sliced_b200 as S
+    monkeypatch.delenv("SLICED_GEMM_TC_FORCE", raising=False)
+    if mode == "3xf16":
+        monkeypatch.setenv("SLICED_GEMM_F16_STRICT", "1")
+    ctx = S.Context(0)
+    md = MODES[mode]
+    n = size
+    rng = np.random.default_rng(42 + size)
+    a, b = _rand32(rng, n * n), _rand32(rng, n * n)
+    da, db = ctx.array(a), ctx.array(b)
+    A, B = a.reshape(n, n), b.reshape(n, n)
+    rows, cols = _sample_idx(rng, n, n)
+    for name, ta, tb in (("NN", 0, 0), ("NT", 0, 1), ("TN", 1, 0)):
+        c = ctx.gemm_ex(ta, tb, n, n, n, da, db, mode=md).numpy().reshape(n, n)
+        A64 = (A[:, rows].T if ta else A[rows]).astype(np.float64)
+        B64 = (B[cols].T if tb else B[:, cols]).astype(np.float64)
+        got = c[np.ix_(rows, cols)]
+        if mode == "tf32":
+            err = np.max(np.abs(got - A64 @ B64))
+            assert err <= 8 * np.sqrt(n) * 2.0 ** -11, (name, err)
+        else:
+            _check_sampled(got, A64, B64, n, rows, cols, what=f"{name} {size} {mode}")
+        del c
+    ctx.close()

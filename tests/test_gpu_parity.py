@@ -82,6 +82,30 @@ def test_binary_ew_and_grad(be, ob, dt, n, op):
     exact(a[1], b[1], "rhs_grad only")
 
 
+@pytest.mark.parametrize("dt", ["f32", "i32"])
+@pytest.mark.parametrize("op", [O.ADD, O.SUB, O.MUL, O.DIV])
+def test_binary_ew_grad_same_buffer_for_both_grads(be, dt, op):
+    """x.mul(x) / add(x, x): lhs_grad and rhs_grad are ONE buffer; the reference's loop adds both contributions in turn
+    (binary_ew/grad/cpu_stack.rs:54-59).  Bit-exact vs the oracle called with the same aliased array."""
+    import sliced_b200 as S
+    ctx = be.ctx
+    rng = np.random.default_rng(5 + op)
+    for n in (1, 5, 4099, 262147):
+        x, og, g0 = rnd(rng, n, dt), rnd(rng, n, dt), rnd(rng, n, dt)
+        if op == O.DIV:
+            x = np.where(np.abs(x) < (1 if dt == "i32" else 0.05), DT[dt](3), x).astype(DT[dt])
+        ref = g0.copy()
+        O.binary_ew_grad(op, x, x, ref, ref, og)
+        dg, dx = ctx.array(g0), ctx.array(x)
+        ctx.binary_ew_grad(op, dx, dx, dg, dg, ctx.array(og))
+        exact(dg.numpy(), ref, f"aliased grads op {op} n {n}")
+        ref2 = g0.copy()
+        O.add_ew_grad(ref2, ref2, og)
+        dg2 = ctx.array(g0)
+        ctx.add_ew_grad(dg2, dg2, ctx.array(og))
+        exact(dg2.numpy(), ref2, "aliased add_ew_grad")
+
+
 def test_misaligned_pointers(be):
     """sub-buffers that start 4 bytes into an allocation take the scalar path and still match"""
     import sliced_b200 as S
@@ -369,3 +393,70 @@ def test_full_size_softmax_rows_sum_to_one(be, big):
     assert float(ctx.max(ctx.unary(0, xg))) <= (4 * C * 2.0 ** -24) ** 2
     row = ctx.softmax(1, C, dx.view(5 * C, C)).numpy()    # one row against the oracle
     assert np.max(np.abs(row - O.softmax(1, C, x[5 * C:6 * C].copy()))) <= 4 * C * 2.0 ** -24 * row.max() + 1e-9
+
+
+def _cce_chain_oracle(samples, features, z, y, labels, rows):
+    """examples/nn.rs:190-233 tail replayed with the oracle's single ops (the reference's operation order)"""
+    s = O.softmax(samples, features, z)
+    preds = O.binary_ew(O.MUL, O.unary(O.UN_CLIP, s, 1e-7, 1. - 1e-7), y)
+    loss = O.unary(O.UN_NEG_LN, O.sum_cols(features, preds))
+    g = O.unary(O.UN_NEG_DIV_SCALAR, O.binary_ew(O.DIV, y, s), float(rows))
+    dz = np.zeros_like(z)
+    O.softmax_grad(samples, features, dz, s, g, closed=True)
+    correct = int(np.sum(np.argmax(s.reshape(samples, features), axis=1) == labels))
+    return s, dz, loss, correct
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64"])
+@pytest.mark.parametrize("shape", [(1, 10), (7, 3), (1000, 10), (65536, 10), (333, 16), (100, 32), (5, 1)])
+def test_softmax_cce_fused_equals_chain(be, dt, shape):
+    """sl_softmax_cce (one launch) against the nine-launch chain it replaces — BIT-IDENTICAL for features <= 32 — and against
+    the oracle's op-by-op replay (exact loss/accuracy structure, libm-level tolerance on values)"""
+    import sliced_b200 as S
+    ctx = be.ctx
+    samples, features = shape
+    rng = np.random.default_rng(samples + features)
+    z = rnd(rng, samples * features, dt, -4, 4)
+    labels = rng.integers(0, features, samples).astype(np.int32)
+    y = np.zeros((samples, features), DT[dt]); y[np.arange(samples), labels] = 1; y = y.ravel()
+    rows = 4 * samples   # global batch under data parallelism
+    dz_, dy, dl = ctx.array(z), ctx.array(y), ctx.array(labels)
+    probs, dz, loss, correct = ctx.softmax_cce(samples, features, dz_, dy, dl, rows)
+    # the chain, through the same C ABI
+    s = ctx.softmax(samples, features, dz_)
+    t = ctx.binary_ew(S.MUL, ctx.unary(S.UN_CLIP, s, 1e-7, 1. - 1e-7), dy)
+    loss_c = ctx.unary(S.UN_NEG_LN, ctx.sum_cols(features, t))
+    g = ctx.unary(S.UN_NEG_DIV_SCALAR, ctx.binary_ew(S.DIV, dy, s), float(rows))
+    dz_c = ctx.array(rnd(rng, samples * features, dt))
+    ctx.softmax_grad(samples, features, dz_c, s, g)
+    exact(probs.numpy(), s.numpy(), "probs")
+    exact(loss.numpy(), loss_c.numpy(), "loss")
+    exact(dz.numpy(), dz_c.numpy(), "dz")
+    assert correct == ctx.count_correct(samples, features, s, dl)
+    # the oracle
+    so, dzo, lo, co = _cce_chain_oracle(samples, features, z, y, labels, rows)
+    rel = 1e-6 if dt == "f32" else 1e-13
+    close_rel(probs.numpy(), so, rel, "probs vs oracle")
+    close_rel(loss.numpy(), lo, rel * 4, "loss vs oracle")
+    assert np.max(np.abs(dz.numpy() - dzo)) <= rel * 8 * max(np.max(np.abs(dzo)), 1e-30)
+    if dt == "f64":
+        assert correct == co
+
+
+@pytest.mark.parametrize("shape", [(64, 1000), (48, 16384), (5, 33)])
+def test_softmax_cce_fused_wide_rows(be, shape):
+    """features > 32: block-per-row form, K-scaled tolerance against the oracle's replay; soft (non one-hot) targets"""
+    ctx = be.ctx
+    samples, features = shape
+    rng = np.random.default_rng(features)
+    z = rnd(rng, samples * features, "f32", -3, 3)
+    y = rng.uniform(0, 1, (samples, features)).astype(np.float32)
+    y = (y / y.sum(1, keepdims=True)).astype(np.float32).ravel()
+    labels = rng.integers(0, features, samples).astype(np.int32)
+    probs, dz, loss, correct = ctx.softmax_cce(samples, features, ctx.array(z), ctx.array(y), ctx.array(labels), samples)
+    so, dzo, lo, co = _cce_chain_oracle(samples, features, z, y, labels, samples)
+    tol = 4 * features * EPS["f32"]
+    assert np.max(np.abs(probs.numpy() - so)) <= tol * np.max(so)
+    assert np.max(np.abs(loss.numpy() - lo)) <= tol * np.max(np.abs(lo)) + 1e-6
+    assert np.max(np.abs(dz.numpy() - dzo)) <= tol * max(np.max(np.abs(dzo)), 1e-30) + 1e-9
+    assert correct == int(np.sum(np.argmax(probs.numpy().reshape(samples, features), axis=1) == labels))

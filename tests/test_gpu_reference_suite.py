@@ -64,6 +64,35 @@ def test_mul(device):
     assert rhs.grad().read().tolist() == [1, 2, 3, 4, 5]
 
 
+def test_mul_by_itself_and_add_to_itself(device):
+    """x.mul(&x) -> 2 x og, add(&x, &x) -> 2 og: both grad closures hit the same gradient buffer (ops.rs:125-126,163-164 on an
+    aliased operand; custos hands out one grad buffer per id)"""
+    x = device.buffer([1, 2, 3, 4, 5], np.int32)
+    out = device.mul(x, x)
+    assert out.read().tolist() == [1, 4, 9, 16, 25]
+    out.backward()
+    assert x.grad().read().tolist() == [2, 4, 6, 8, 10]
+    y = device.buffer([1., -2., 3.5], np.float32)
+    out = device.add(y, y)
+    out.backward()
+    assert y.grad().read().tolist() == [2., 2., 2.]
+    z = device.buffer([4., 5.], np.float32)
+    out = device.sub(z, z)
+    out.backward()
+    assert z.grad().read().tolist() == [0., 0.]
+
+
+def test_gradients_of_dropped_buffers_are_released(device):
+    """a non-Cached device allocates a fresh buffer (and, in backward, a fresh gradient) per op: the gradient map must not keep
+    them alive once the buffers are gone (custos drops them with the buffer, OnDropBuffer †)"""
+    x = device.buffer(np.ones(1024, np.float32))
+    for _ in range(5):
+        out = device.square(device.mul(x, x))
+        out.backward()
+        del out
+    assert device.n_grads() <= 2, device.n_grads()
+
+
 def test_pow(device):
     """tests/test_pow.rs:6-21 (f64, exact)"""
     x = device.buffer([1., 2., 3., 4., 5.], np.float64)
