@@ -66,7 +66,9 @@ def peaks():
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
     of this very command (profiles/r1_ncu_traffic.json, written from the .ncu-rep by tools/ncu_summary.py); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
     try:
         d = json.load(open(p))
         return dict(bytes_per_launch=d["dram_bytes_per_launch"], unit="B", kernel=d["kernel"], algorithmic_bytes_per_launch=d.get("algorithmic_bytes_per_launch"),
@@ -185,7 +187,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), min(args.warmup, 1)
+    # the FULL workload (global batch 65536, ~15-20 s of host time per step) on every host core: a bounded number of steps keeps the
+    # run inside a few minutes; --cpu-sample N shrinks the batch (then config.sample_batch says so)
+    steps, warmup = max(1, min(args.steps, 3 if args.cpu_sample >= GLOBAL_BATCH else 5)), min(args.warmup, 1)
     cb, dt = cpu_reference_rate(steps, warmup, args.cpu_sample)
     line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup, ms_per_step=dt * 1e3,
                 higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
@@ -196,6 +200,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
+    rc_fail = False
     import torch
     import torch.distributed as dist
 
@@ -221,13 +226,8 @@ def run_ours(args):
     ctx = dev.ctx_handle
 
     if world > 1:  # one NCCL communicator for the gradient exchange, id shipped through torch.distributed
-        idbuf = (C.c_char * 128)()
-        if rank == 0:
-            capi.check(None, lib.sl_comm_unique_id(idbuf))
-        t = torch.frombuffer(bytearray(bytes(idbuf)), dtype=torch.uint8).cuda()
-        dist.broadcast(t, 0)
-        idb = bytes(t.cpu().numpy().tobytes())
-        capi.check(ctx, lib.sl_comm_init_rank(ctx, world, rank, idb))
+        from sliced_b200 import dp
+        dp.init_comm(lib, ctx, dist, rank, world)
 
     batch = GLOBAL_BATCH // world if args.scaling == "strong" else GLOBAL_BATCH
     if args.debug_per_gpu_batch:   # diagnosis only (e.g. the per-GPU share of an 8-GPU run on one GPU); the line says so in config
@@ -270,6 +270,60 @@ def run_ours(args):
 
     def resident_step(metrics: bool):
         return mlp.step(bx, by, bl, batch, LR, grad_rows=global_batch, want_metrics=metrics)
+
+    # ---------------- self-check at the headline configuration, before anything is timed
+    # (a) the default arithmetic (3xFP16 tensor-core gemms, fused epilogues) against SL_GEMM_SIMT from identical weights: the SIMT
+    #     gemm is the kernel the parity tests hold BIT-IDENTICAL to the oracle's restatement (tests/test_gpu_gemm.py), so this ties
+    #     the benchmarked step to the oracle at the full 65536 x 4096 x 4096 / K = 65536 shapes;
+    # (b) under data parallelism: the all-reduced bucket of the N ranks against the gradient one GPU computes on the whole global
+    #     batch (rel 1e-5); after the timed steps, the parameters of all ranks must be bit-identical.
+    parity = None
+    if not args.no_parity_check:
+        def grads(mode):
+            dev.set_gemm_mode(mode)
+            l, c_ = mlp.forward_backward(bx, by, bl, batch, grad_rows=global_batch)
+            mlp.allreduce_grads()
+            return l, c_, mlp.grad_bucket().read()
+        l_ref, c_ref, g_ref = grads(S.GEMM_SIMT)
+        l_got, c_got, g_got = grads({"tf32": S.GEMM_TF32, "3xtf32": S.GEMM_3XTF32, "3xf16": S.GEMM_3XF16}[args.gemm_mode])
+        gmax = float(np.max(np.abs(g_ref)))
+        gdiff = float(np.max(np.abs(g_got - g_ref)))
+        tol_g = 1e-4 if args.gemm_mode != "tf32" else 5e-2
+        parity = dict(reference="SL_GEMM_SIMT step (CUDA-core fp32, bit-identical to the oracle's gemm restatement) from the same weights and batch",
+                      loss_sum_ref=l_ref, loss_sum=l_got, loss_rel_diff=abs(l_got - l_ref) / max(abs(l_ref), 1e-30),
+                      correct_ref=int(c_ref), correct=int(c_got), grad_entries_compared=int(g_ref.size), grad_max_abs=gmax,
+                      grad_max_abs_diff=gdiff, grad_rel_diff=gdiff / max(gmax, 1e-30), tol_grad_rel=tol_g, tol_loss_rel=1e-5 if args.gemm_mode != "tf32" else 1e-2)
+        parity["ok"] = bool(parity["loss_rel_diff"] <= parity["tol_loss_rel"] and parity["grad_rel_diff"] <= tol_g and
+                            abs(c_got - c_ref) <= max(2, batch // 1000) and np.all(np.isfinite(g_got)))
+        if world > 1:
+            if rank == 0:   # one GPU, whole global batch, a second device WITHOUT a communicator (no collective on this path)
+                dev1 = CUDA(local_rank, cached=True, stream=stream.cuda_stream)
+                dev1.set_gemm_mode({"tf32": S.GEMM_TF32, "3xtf32": S.GEMM_3XTF32, "3xf16": S.GEMM_3XF16}[args.gemm_mode])
+                m1 = Mlp(dev1, DIMS, 0)
+                m1.set_fused(not args.unfused)
+                for l in range(len(DIMS) - 1):
+                    m1.weights(l).write(W[l]); m1.bias(l).write(B[l])
+                xs, ys, ls = [], [], []
+                for r in range(world):
+                    gr = torch.Generator(device="cuda").manual_seed(7 + r)
+                    xs.append(torch.empty(batch, DIMS[0], device="cuda").uniform_(0, 1, generator=gr))
+                    lr_ = torch.randint(0, DIMS[-1], (batch,), device="cuda", generator=gr, dtype=torch.int32)
+                    yr = torch.zeros(batch, DIMS[-1], device="cuda"); yr[torch.arange(batch, device="cuda"), lr_.long()] = 1.0
+                    ys.append(yr); ls.append(lr_)
+                xg, yg, lg = torch.cat(xs), torch.cat(ys), torch.cat(ls)
+                del xs, ys, ls
+                torch.cuda.synchronize()
+                l1, c1 = m1.forward_backward(dev1.wrap(xg.data_ptr(), xg.numel()).no_grad(), dev1.wrap(yg.data_ptr(), yg.numel()).no_grad(),
+                                             dev1.wrap(lg.data_ptr(), global_batch, np.int32), global_batch, grad_rows=global_batch)
+                g1 = m1.grad_bucket().read()
+                d1 = float(np.max(np.abs(g_got - g1)))
+                parity["dp"] = dict(ranks=world, one_gpu_global_batch_vs_allreduced_bucket_rel=d1 / max(float(np.max(np.abs(g1))), 1e-30), tol=1e-5)
+                parity["ok"] = bool(parity["ok"] and parity["dp"]["one_gpu_global_batch_vs_allreduced_bucket_rel"] <= 1e-5)
+                del m1, xg, yg, lg
+                dev1.close()
+                torch.cuda.empty_cache()
+        for l in range(len(DIMS) - 1):   # forward_backward does not touch the parameters; rewrite them anyway: the timed run starts from W
+            mlp.weights(l).write(W[l]); mlp.bias(l).write(B[l])
 
     # ---------------- device-resident leg (`value`)
     sampler = ClockSampler(local_rank)
@@ -361,6 +415,28 @@ def run_ours(args):
             f.write(f"# {'kernel':60s} launches/step   ms/step   share\n")
             for name, n, ms in rows:
                 f.write(f"{name[:62]:62s} {int(n) / bsteps:8.1f} {float(ms) / bsteps:10.4f} {100 * float(ms) / bsteps / tot:7.2f}%\n")
+    if world > 1 and parity is not None:   # replicas bit-identical across ranks after all the steps above (same summed gradients everywhere)
+        import zlib
+        crc = zlib.crc32(mlp.params().read().tobytes())
+        t = torch.tensor([crc], device="cuda", dtype=torch.int64)
+        allc = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allc, t)
+        same = all(int(a.item()) == crc for a in allc)
+        if rank == 0:
+            parity["dp"]["replica_param_crc32_identical_across_ranks"] = bool(same)
+            parity["ok"] = bool(parity["ok"] and same)
+    sweeps_out = None
+    if rank == 0 and world == 1 and not args.no_sweeps:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sweeps as SW
+        del mlp   # free the step's activations before the 16384^2 sweeps
+        mlp = None
+        stage.clear()
+        torch.cuda.empty_cache()
+        try:
+            sweeps_out = SW.run_all(local_rank, args.sweep_budget)
+        except Exception as e:   # a sweep failure must not lose the headline line
+            sweeps_out = dict(error=repr(e))
     if rank == 0:
         pk = peaks()
         f16 = args.gemm_mode == "3xf16"
@@ -389,14 +465,23 @@ def run_ours(args):
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline,
                     training=dict(first_step_mean_loss=first_loss, last_step_mean_loss=loss_sum / batch, last_step_accuracy=correct / batch,
                                   init="W ~ U(-a, a), a = min(0.1, sqrt(6/(fan_in+fan_out))); b = 0"))
+        if parity is not None:
+            line["parity_check"] = parity
+        if sweeps_out is not None:
+            line["sweeps"] = sweeps_out
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_reference_rate(1, 0, args.cpu_sample)
+            cb, _ = cpu_reference_rate(1, 0, args.cpu_sample)   # one full-batch step: ~15-20 s of host time
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["ok"]:
+            print("PARITY CHECK FAILED: " + json.dumps(parity), file=sys.stderr, flush=True)
+            rc_fail = True
     del mlp
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rc_fail:
+        raise SystemExit(3)
 
 
 def main():
@@ -409,7 +494,10 @@ def main():
     ap.add_argument("--debug-per-gpu-batch", type=int, default=0, help="diagnosis only: override the per-GPU batch (not the BASELINE workload)")
     ap.add_argument("--breakdown", default=None, help="write an in-situ per-kernel time table of the step to this path")
     ap.add_argument("--gemm-mode", choices=["3xtf32", "tf32", "3xf16"], default="3xf16")
-    ap.add_argument("--cpu-sample", type=int, default=2048, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=GLOBAL_BATCH, help="batch of the CPU legs (default: the full global batch; smaller = a bounded sample)")
+    ap.add_argument("--no-sweeps", action="store_true", help="skip the configs[0..3] sweeps appended to the N=1 line")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--sweep-budget", type=float, default=60.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="run the op-by-op tape instead of the fused-epilogue step (bit-identical results)")
     args = ap.parse_args()

@@ -1,0 +1,48 @@
+"""
+SURVEY 8(e) "Parity", on hardware: N ranks (one process per GPU, NCCL over NVLink) train batch shards with the fused device step;
+  * the all-reduced gradient bucket equals the gradient ONE GPU computes on the whole batch (rel 1e-5 per step),
+  * after k steps every rank holds bit-identical parameters (crc32 all-gathered),
+  * and the parameters / losses / accuracy follow the CPU oracle's replay of the same global step (rel 2e-5).
+Needs >= 2 GPUs (skipped on a single-GPU box; `bench.py --gpus N` runs the same checks at the headline size as `parity_check.dp`).
+"""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("dims,batch,chunks", [([512, 768, 512, 10], 4096, "1"), ([2048, 4864, 512, 10], 4096, "4")])
+def test_two_rank_step_matches_one_gpu_and_oracle(tmp_path, dims, batch, chunks):
+    import sliced_b200 as S
+    n = S.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    out = tmp_path / "dp.json"
+    env = dict(os.environ, SLICED_DP_CHUNKS=chunks)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_worker.py"), str(out), json.dumps(dims), str(batch), "3", "0.1"]
+    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert p.returncode == 0, p.stdout[-4000:]
+    r = json.load(open(out))
+    assert r["bucket_rel_diff_vs_one_gpu"] <= 1e-5, r
+    assert r["crc_identical_across_ranks"], r
+    assert r["params_rel_diff_vs_one_gpu"] <= 1e-5, r
+    assert r["params_rel_diff_vs_oracle"] <= 2e-5, r
+    for a, b in zip(r["loss_dp"], r["loss_oracle"]):
+        assert abs(a - b) <= 2e-5 * abs(b), r
+    assert r["correct_dp"] == r["correct_oracle"], r

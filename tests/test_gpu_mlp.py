@@ -269,3 +269,41 @@ def test_graph_replay_equals_eager_sine_net():
     assert res[0][0] == res[1][0]
     assert np.array_equal(res[0][1], res[1][1])
     assert res[1][2] < res[0][2] / 4, "replay should need far fewer launches than the eager tape"
+
+
+def test_sine_net_1000_steps_against_fp64_yardstick_and_teacher_forced_parity():
+    """examples/sine_net.rs at the shipped length (1000 iterations).
+    The trajectory is chaotic (tests/sine_replay.py, tests/test_oracle_golden.py::test_sine_net_trajectory_is_chaotic_evidence: two
+    CPU fp32 implementations end 5.6e-2 apart), so the end-to-end gate is the fp64 replay with the measured fp32 spread (10 %),
+    and PARITY is shown step by step: restarted from the oracle's own weights at steps 0, 100, ..., 1000 the device step reproduces
+    the oracle's loss to 2e-6 and its next weights to 1e-5 — per-step agreement everywhere along the trajectory."""
+    from sliced_b200.host import CUDA, Mlp
+    from tests import sine_replay as SR
+    xs, ys, W, B = SR.problem()
+    dims = SR.DIMS
+    # the device, 1001 steps from the common initialisation
+    hist, _, _, _ = run_gpu(dims, 1, xs, ys, None, W, B, 1e-4, 1001)
+    gpu = np.array([h[0] for h in hist])
+    l64 = SR.replay(np.float64, 1001, W, xs, ys)
+    assert np.all(np.abs(gpu[:10] - l64[:10]) <= 1e-5 * l64[:10])
+    print(f"sine_net loss after 1001 steps: gpu {gpu[1000] / 1000:.6f} fp64 {l64[1000] / 1000:.6f} rel {abs(gpu[1000] - l64[1000]) / l64[1000]:.3e}")
+    assert abs(gpu[1000] - l64[1000]) <= 0.10 * l64[1000]
+    assert gpu[1000] < 0.02 * gpu[0]
+    # teacher-forced single steps along the oracle's trajectory
+    Wo, Bo = [w.copy() for w in W], [b.copy() for b in B]
+    dev = CUDA(0, cached=True)
+    mlp = Mlp(dev, dims, 1)
+    dx, dy = dev.buffer(xs).no_grad(), dev.buffer(ys).no_grad()
+    for k in range(1001):
+        if k % 100 == 0:
+            for l in range(3):
+                mlp.weights(l).write(Wo[l]); mlp.bias(l).write(Bo[l])
+            l_gpu = mlp.step(dx, dy, None, 1000, 1e-4)[0]
+        l_ref = O.mlp_step(1, dims, xs, ys, None, Wo, Bo, 1e-4)[0]
+        if k % 100 == 0:
+            assert abs(l_gpu - l_ref) <= 2e-6 * abs(l_ref), (k, l_gpu, l_ref)
+            for l in range(3):
+                assert np.max(np.abs(mlp.weights(l).read() - Wo[l])) <= 1e-5 * np.max(np.abs(Wo[l])), (k, l)
+                assert np.max(np.abs(mlp.bias(l).read() - Bo[l])) <= 1e-5 * max(np.max(np.abs(Bo[l])), 1e-3), (k, l)
+    del mlp, dx, dy
+    dev.close()
