@@ -13,7 +13,7 @@ SGD, exactly the op sequence of examples/nn.rs:184-237, run through the C++ host
 
 value   whole-job samples/s with the batch already resident in HBM (device-timed with CUDA events, max over ranks)
 e2e     the same metric through the host-layer API with HOST buffers: every step copies its inputs from pinned host memory
-        and reads the step's loss/accuracy back
+        and copies the step's loss/accuracy back to (pinned) host memory
 roofline      the dominant kernel (tcgen05 gemm): per-launch CUDA events recorded live during the timed steps
 cpu_baseline  the reference's CPU path (oracle replay + OpenBLAS sgemm, what custos' `blas` feature links) on the host cores,
               on a bounded sample of the same workload — a reported baseline, not the target
@@ -372,6 +372,9 @@ def run_ours(args):
         capi.check(ctx, lib.sl_write_prefetch(ctx, sy.ptr, y_pin.data_ptr(), y_pin.numel() * 4))
         capi.check(ctx, lib.sl_write_prefetch(ctx, sl_.ptr, l_pin.data_ptr(), l_pin.numel() * 4))
 
+    met_pin = torch.zeros(2 * (args.steps + 4), dtype=torch.float32, pin_memory=True)   # [loss_sum f32 | correct i32] per step
+    met_ptr = mlp.metrics_ptr
+
     def e2e_run(nsteps):
         upload(0)
         for i in range(nsteps):
@@ -379,7 +382,9 @@ def run_ours(args):
             if i + 1 < nsteps:
                 upload((i + 1) & 1)                     # batch i+1 goes up while step i runs
             sx, sy, sl_ = stage[i & 1]
-            mlp.step(sx, sy, sl_, batch, LR, grad_rows=global_batch, want_metrics=True)
+            mlp.step(sx, sy, sl_, batch, LR, grad_rows=global_batch, want_metrics=False)
+            # every step's loss / accuracy goes to (pinned) host memory, stream-ordered, without stalling the next launch
+            capi.check(ctx, lib.sl_read_async(ctx, met_pin.data_ptr() + 8 * i, met_ptr, 8))
 
     e2e_run(2)
     barrier()
@@ -388,6 +393,8 @@ def run_ours(args):
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    e2e_losses = met_pin[0:2 * args.steps:2].clone()
+    assert bool(torch.isfinite(e2e_losses).all()) and float(e2e_losses.min()) > 0, "e2e leg: a step's loss did not arrive on the host"
     barrier()
 
     if args.breakdown:

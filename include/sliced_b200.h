@@ -141,6 +141,9 @@ int sl_prefetch_wait(sl_ctx* ctx);
 int sl_prefetch_release(sl_ctx* ctx);
 /* ref: custos `Read::read` † — device -> host, blocks until the data is on the host */
 int sl_read(sl_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+/* Non-blocking variant: ordered on the ctx stream, destination must be pinned (sl_host_alloc); the bytes are valid on the host after
+ * the next sl_sync / sl_read.  Lets a training loop fetch every step's loss without stalling the launch of the next step. */
+int sl_read_async(sl_ctx* ctx, void* dst_host_pinned, const void* src_dev, size_t bytes);
 /* ref: custos `CloneBuf` / `WriteBuf::write_buf` † — device -> device */
 int sl_copy(sl_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
 /* ref: custos `ClearBuf::clear` † / `Gradients::zero_grad` (examples/nn.rs:186-188) */

@@ -80,6 +80,7 @@ def _declare(lib):
         "sl_host_free": ([_vp, _vp], _i),
         "sl_write": ([_vp, _vp, _vp, _sz], _i),
         "sl_read": ([_vp, _vp, _vp, _sz], _i),
+        "sl_read_async": ([_vp, _vp, _vp, _sz], _i),
         "sl_write_prefetch": ([_vp, _vp, _vp, _sz], _i),
         "sl_prefetch_wait": ([_vp], _i),
         "sl_prefetch_release": ([_vp], _i),

@@ -4,6 +4,7 @@
 // libnccl is dlopen'ed at first use (the torch-bundled libnccl.so.2 when the process already loaded it, else the
 // system one), so that libsliced_b200.so itself loads on a box without NCCL or without a GPU.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -95,6 +96,7 @@ int sl_allreduce_sum(sl_ctx* ctx, int dtype, void* buf, size_t n) {
         if (ctx->nranks <= 1) return SL_OK;  // a world of one: the sum over ranks is the buffer itself
         return sl_set_error(ctx, SL_ERR_NCCL, "sl_allreduce_sum: communicator not initialised");
     }
+    if (getenv("SLICED_DP_NOCOMM")) return SL_OK;   // diagnosis only (tools/dp_sweep.py): the step without its exchange
     const int dt = nccl_dtype(dtype);
     SL_NCCL(ctx, nccl().AllReduce(buf, buf, n, dt, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return SL_OK;
@@ -112,6 +114,7 @@ int sl_allreduce_sum_async(sl_ctx* ctx, int dtype, void* buf, size_t n) {
         if (ctx->nranks <= 1) return SL_OK;
         return sl_set_error(ctx, SL_ERR_NCCL, "sl_allreduce_sum_async: communicator not initialised");
     }
+    if (getenv("SLICED_DP_NOCOMM")) return SL_OK;
     if (!ctx->comm_stream) {
         SL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
         SL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->comm_ready, cudaEventDisableTiming));

@@ -297,6 +297,16 @@ int sl_read(sl_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
     return SL_OK;
 }
 
+// device -> (pinned) host without blocking: the copy is ordered on the ctx stream like any op; the data is on the host after the
+// next sl_sync / sl_read.  A training loop reads each step's loss this way without stalling the launch of the next step.
+int sl_read_async(sl_ctx* ctx, void* dst_host_pinned, const void* src_dev, size_t bytes) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    if (bytes == 0) return SL_OK;
+    SL_REQUIRE(ctx, dst_host_pinned && src_dev, "NULL pointer");
+    SL_CUDA(ctx, cudaMemcpyAsync(dst_host_pinned, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SL_OK;
+}
+
 int sl_copy(sl_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     sl_note_writes(ctx, dst_dev);

@@ -828,6 +828,19 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             const int kb0 = split * kbs, kb1 = min(num_kb, kb0 + kbs);
             const int num_chunks = chunk_count(kb1 - kb0);
             float acc[CPW];
+            // The store phase reads the relu-mask source (dX of the MLP) or the old C (+=) of this warp's 32 x 128 slice straight from
+            // global memory; ncu showed those loads stalling the epilogue warps (which then cannot drain TMEM: 67.6 % tensor-pipe
+            // activity on dX vs 93 % on dW).  Pull the slice into L2 now, while the mainloop of this tile runs: one bulk prefetch per row.
+            if (p.c_vec_ok && (p.mask_src || p.accumulate)) {
+                const int prow = m_blk * Cfg::TILE_M + (int)rank * 128 + quad * 32 + lane;
+                const int pn0 = n_blk * Cfg::TILE_N + col0;
+                const int pcols = min(CPW, p.N - pn0);
+                if (prow < p.M && pcols > 0) {
+                    const float* src = p.mask_src ? p.mask_src + (size_t)prow * p.N + pn0
+                                                  : p.C + (size_t)split * p.M * p.N + (size_t)prow * p.N + pn0;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(pcols * 4)) : "memory");
+                }
+            }
             for (int ch = 0; ch < num_chunks; ++ch, ++g) {
                 const uint32_t buf = g & 1;
                 mbar_wait(tmem_full_bar(buf), (g >> 1) & 1);

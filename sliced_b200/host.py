@@ -63,6 +63,7 @@ def _lib():
             "slh_mlp_new": ([_vp, _i, P(_sz), _i], _vp),
             "slh_mlp_free": ([_vp], None),
             "slh_mlp_n_params": ([_vp], _sz),
+            "slh_mlp_metrics_dptr": ([_vp], _vp),
             "slh_mlp_weights": ([_vp, _i], _vp),
             "slh_mlp_bias": ([_vp, _i], _vp),
             "slh_mlp_grad_bucket": ([_vp], _vp),
@@ -317,6 +318,10 @@ class Mlp:
     def n_layers(self): return len(self.dims) - 1
     @property
     def n_params(self): return _lib().slh_mlp_n_params(self.h)
+    @property
+    def metrics_ptr(self) -> int:
+        """device address of the last step's [loss_sum f32][correct i32] (fetch with sl_read_async to avoid a blocking read per step)"""
+        return _lib().slh_mlp_metrics_dptr(self.h) or 0
     def weights(self, l) -> Buffer: return Buffer(self.device, _lib().slh_mlp_weights(self.h, l))
     def bias(self, l) -> Buffer: return Buffer(self.device, _lib().slh_mlp_bias(self.h, l))
     def grad_bucket(self) -> Buffer: return Buffer(self.device, _lib().slh_mlp_grad_bucket(self.h))

@@ -157,6 +157,7 @@ slh_mlp* slh_mlp_new(slh_device* d, int n_dims, const size_t* dims, int loss_kin
 }
 void slh_mlp_free(slh_mlp* m) { delete (Mlp*)m; }
 size_t slh_mlp_n_params(slh_mlp* m) { return ((Mlp*)m)->n_params(); }
+void* slh_mlp_metrics_dptr(slh_mlp* m) { return ((Mlp*)m)->metrics_dptr(); }
 slh_buffer* slh_mlp_weights(slh_mlp* m, int layer) { return (slh_buffer*)wrap_handle(((Mlp*)m)->layer(layer).weights.data); }
 slh_buffer* slh_mlp_bias(slh_mlp* m, int layer) { return (slh_buffer*)wrap_handle(((Mlp*)m)->layer(layer).bias.data); }
 slh_buffer* slh_mlp_grad_bucket(slh_mlp* m) { return (slh_buffer*)wrap_handle(((Mlp*)m)->grad_bucket()); }

@@ -47,6 +47,7 @@ class Mlp {
     Buf grad_bucket() { return bucket_; }
     Buf params() { return params_; }
     size_t n_params() const { return n_params_; }
+    void* metrics_dptr() const { return metrics_dev_; }   // device [loss_sum f32][correct i32] of the last step (for sl_read_async)
 
     // One training step, op by op like the reference.  x: [batch x dims[0]] (no_grad), y: [batch x dims.back()],
     // labels: int32 [batch] or null.  grad_rows: the `rows` of cce_grad (nn.rs:151) — the global batch under DP.

@@ -470,3 +470,40 @@ def test_cube_sweep_sizes_sampled(size, mode, monkeypatch):
             _check_sampled(got, A64, B64, n, rows, cols, what=f"{name} {size} {mode}")
         del c
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "3xf16"])
+def test_plane_scope_sees_non_gemm_writes(mode, monkeypatch):
+    """Inside a gemm scope cached operand planes / column scales must die when ANY library call rewrites the buffer (element-wise
+    op in place, sl_write, sl_clear, sgd) — not only when a gemm does: results stay bit-identical to the unscoped sequence."""
+    import sliced_b200 as S
+    monkeypatch.delenv("SLICED_GEMM_TC_FORCE", raising=False)
+    md = MODES[mode]
+    ctx = S.Context(0)
+    m, k, n = 2048, 2304, 2560   # >= 37 pair tiles: 2-CTA kernel, MN-major operands, 3xFP16 eligible
+    rng = np.random.default_rng(8)
+    xh, wh, gh = _rand32(rng, m * k), _rand32(rng, k * n), _rand32(rng, m * n)
+    x2h = _rand32(rng, m * k)
+
+    def sequence(scoped):
+        x, w, g = ctx.array(xh), ctx.array(wh), ctx.array(gh)
+        if scoped:
+            ctx.gemm_scope_begin()
+        outs = [ctx.gemm(m, k, n, x, w, mode=md)]            # x row-split (leaves its column scales in the scope), w cached
+        ctx.unary(S.UN_MUL_SCALAR, x, 3.0, 0.0, out=x)        # in-place element-wise write to x
+        outs.append(ctx.gemm_tn(k, n, m, x, g, mode=md))      # must see 3x (column scales of the OLD x are stale)
+        outs.append(ctx.gemm(m, k, n, x, w, mode=md))
+        x.write(x2h)                                          # sl_write
+        outs.append(ctx.gemm(m, k, n, x, w, mode=md))
+        ctx.sgd_step(w, ctx.array(wh), 0.5)                   # w -= 0.5 w
+        outs.append(ctx.gemm(m, k, n, x, w, mode=md))
+        x.clear()                                             # sl_clear
+        outs.append(ctx.gemm(m, k, n, x, w, mode=md))
+        if scoped:
+            ctx.gemm_scope_end()
+        return [o.numpy() for o in outs]
+    plain, scoped = sequence(False), sequence(True)
+    for i, (p, s) in enumerate(zip(plain, scoped)):
+        assert np.array_equal(p, s), i
+    assert np.all(plain[-1] == 0)
+    ctx.close()
