@@ -67,18 +67,26 @@ def main(out_path, dims, batch, steps, lr):
         params1 = m1.params().read()
         O.use_openblas(os.cpu_count() or 1)
         Wo, Bo = [w.copy() for w in W], [b.copy() for b in B]
-        ho = [O.mlp_step(0, dims, x.ravel(), y.ravel(), labels, Wo, Bo, lr)[:2] for _ in range(steps)]
-        O.use_naive_gemm()
         seg, off = [], 0
         for i in range(len(dims) - 1):     # flat parameter layout of Mlp: segments padded to 64 floats
             for n in (dims[i] * dims[i + 1], dims[i + 1]):
                 seg.append((off, n)); off += (n + 63) // 64 * 64
-        flat_o = np.zeros_like(params1)
-        for (o, n), p in zip(seg, [p for pair in zip(Wo, Bo) for p in pair]):
-            flat_o[o:o + n] = p
+
+        def flat(ws, bs):
+            f = np.zeros_like(params1)
+            for (o, n), p in zip(seg, [p for pair in zip(ws, bs) for p in pair]):
+                f[o:o + n] = p
+            return f
+        r0 = O.mlp_step(0, dims, x.ravel(), y.ravel(), labels, Wo, Bo, lr, want_grads=True)
+        bucket_o = flat(r0[2], r0[3])
+        ho = [r0[:2]] + [O.mlp_step(0, dims, x.ravel(), y.ravel(), labels, Wo, Bo, lr)[:2] for _ in range(steps - 1)]
+        O.use_naive_gemm()
+        flat_o = flat(Wo, Bo)
         gmax = float(np.max(np.abs(bucket1)))
         rep = dict(world=world, dims=dims, batch=batch, steps=steps,
                    bucket_rel_diff_vs_one_gpu=float(np.max(np.abs(bucket - bucket1))) / gmax,
+                   bucket_rel_diff_vs_oracle=float(np.max(np.abs(bucket - bucket_o))) / gmax,
+                   one_gpu_bucket_rel_diff_vs_oracle=float(np.max(np.abs(bucket1 - bucket_o))) / gmax,
                    params_rel_diff_vs_one_gpu=float(np.max(np.abs(params - params1))) / float(np.max(np.abs(params1))),
                    params_rel_diff_vs_oracle=float(np.max(np.abs(params - flat_o))) / float(np.max(np.abs(flat_o))),
                    crc_identical_across_ranks=all(int(c.item()) == crc for c in allc),

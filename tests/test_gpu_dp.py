@@ -25,7 +25,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("dims,batch,chunks", [([512, 768, 512, 10], 4096, "1"), ([2048, 4864, 512, 10], 4096, "4")])
+@pytest.mark.parametrize("dims,batch,chunks", [([1024, 2560, 1280, 10], 8192, "1"), ([2048, 4864, 1280, 10], 8192, "4")])
 def test_two_rank_step_matches_one_gpu_and_oracle(tmp_path, dims, batch, chunks):
     import sliced_b200 as S
     n = S.device_count()
@@ -39,7 +39,12 @@ def test_two_rank_step_matches_one_gpu_and_oracle(tmp_path, dims, batch, chunks)
     p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
     assert p.returncode == 0, p.stdout[-4000:]
     r = json.load(open(out))
+    # shapes are chosen so that a rank's half batch and the whole batch run the SAME gemm kernel: each sample's forward pass is then
+    # bit-identical in both runs and only the batch-direction sums differ.  (Against another arithmetic — the oracle's sequential
+    # fp32 sums — a handful of pre-activations within 1e-7 of zero flip their relu mask, which moves single gradient entries by
+    # ~1e-5 of the largest one: reported, gated at 1e-4.)
     assert r["bucket_rel_diff_vs_one_gpu"] <= 1e-5, r
+    assert r["bucket_rel_diff_vs_oracle"] <= 1e-4 and r["one_gpu_bucket_rel_diff_vs_oracle"] <= 1e-4, r
     assert r["crc_identical_across_ranks"], r
     assert r["params_rel_diff_vs_one_gpu"] <= 1e-5, r
     assert r["params_rel_diff_vs_oracle"] <= 2e-5, r
