@@ -145,7 +145,19 @@ int sl_comm_wait_n(sl_ctx* ctx, int n) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     if (n <= 0 || !ctx->comm_stream || ctx->comm_issued == 0) return SL_OK;
     const size_t i = (size_t)n < ctx->comm_issued ? (size_t)n : ctx->comm_issued;
+    sl_ctx::ProfRec pr{};
+    const bool prof = ctx->profiling && ctx->profiling_all;
+    if (prof) {   // in-situ breakdown: time the compute stream spends idle waiting for these exchanges
+        cudaEventCreate(&pr.a);
+        cudaEventCreate(&pr.b);
+        pr.name = "(exposed gradient exchange: compute stream waiting in sl_comm_wait_n)";
+        cudaEventRecord(pr.a, ctx->stream);
+    }
     SL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->comm_events[i - 1], 0));
+    if (prof) {
+        cudaEventRecord(pr.b, ctx->stream);
+        ctx->prof.push_back(pr);
+    }
     return SL_OK;
 }
 

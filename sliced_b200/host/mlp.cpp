@@ -153,7 +153,8 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
         fused_batch_ = batch;
     }
     // parameter gradients accumulate (bias: += column sums) -> zero the bucket; activation gradients are all SET
-    d.check(sl_clear(c, bucket_->dptr, bucket_->bytes()));
+    for (size_t l = 0; l < L; ++l)   // (the weight gradients are SET by their gemm; the padding between segments is never written)
+        d.check(sl_clear(c, (float*)bucket_->dptr + seg_off_[2 * l + 1], (seg_off_[2 * l + 2] - seg_off_[2 * l + 1]) * sizeof(float)));
     d.check(sl_clear(c, metrics_dev_, 16));
     // every activation / weight / gz buffer is read by two gemms of this step (forward + a gradient gemm): split each into its
     // TF32 planes once.  Nothing but gemms writes those buffers between here and the end of the backward pass.
