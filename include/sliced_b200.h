@@ -211,6 +211,42 @@ int sl_chained_fwd(sl_ctx* ctx, int dtype, const void* x, const void* b, void* o
 int sl_chained_bwd(sl_ctx* ctx, int dtype, const void* x, const void* b, void* x_grad, void* b_grad,
                    const void* out_grad, size_t n);
 
+/* Fused element-wise chain (SURVEY 8b `sl_fused_chain`): ONE launch evaluates a short straight-line program over n elements — the
+ * device analogue of custos' `Lazy` graph + `optimize()` for chains of element-wise ops (ref: examples/chained_perf.rs:86-114,
+ * examples/sine_net.rs:178-233) and of the arbitrary expression closures custos compiles for apply_fn / add_unary_grad /
+ * binary_ew (ref: src/ops2/binary_ew/mod.rs:55-63, src/ops.rs:36,65,423,438, src/matrix.rs:181,218,246).
+ *
+ * The program works on registers r[0 .. n_regs): r[i] = inputs[i][e] for i < n_in; every instruction writes one register;
+ * output j stores r[out_reg[j]] (SET) or adds it to what the output holds (ACC: out = out + r).  An input may alias an output
+ * (in-place; element-wise so every thread reads before it writes).  Every instruction performs exactly the IEEE operation of the
+ * stand-alone op it replaces (same templates, no contraction), so a fused chain is bit-identical to the launch-per-op sequence;
+ * it moves (n_in + n_out [+ n_out for ACC]) * 4 bytes per element instead of 8-28 bytes per op.  f32 / f64 / i32 (integer
+ * programs may not use the transcendental unary codes). */
+#define SL_CHAIN_MAX_INSTRS 32
+#define SL_CHAIN_MAX_INPUTS 8
+#define SL_CHAIN_MAX_OUTPUTS 4
+#define SL_CHAIN_MAX_REGS 24
+typedef enum sl_chain_op {
+    SL_CH_ADD = 0, SL_CH_SUB = 1, SL_CH_MUL = 2, SL_CH_DIV = 3, /* r[dst] = r[a] op r[b]  (codes of sl_binop) */
+    SL_CH_RDIV_IMM = 4,                                          /* r[dst] = imm0 / r[a]   (d/dl of DIV: 1 / r) */
+    SL_CH_CONST = 5,                                             /* r[dst] = imm0 */
+    SL_CH_COPY = 6,                                              /* r[dst] = r[a] */
+    SL_CH_UNARY_F = 16, /* + sl_unop u: r[dst] = f_u(r[a]; imm0, imm1)   exactly sl_unary */
+    SL_CH_UNARY_D = 48  /* + sl_unop u: r[dst] = g_u(r[a]; imm0, imm1)   the derivative sl_unary_grad multiplies out_grad by */
+} sl_chain_op;
+typedef struct sl_chain_instr {
+    uint8_t op, dst, a, b;
+    uint8_t flags, pad_[3]; /* set by the library (operand forwarding / dead-store elimination); callers leave 0 */
+    double imm0, imm1;
+} sl_chain_instr;
+typedef struct sl_chain_prog {
+    int32_t n_instr, n_in, n_out, n_regs;
+    sl_chain_instr instr[SL_CHAIN_MAX_INSTRS];
+    uint8_t out_reg[SL_CHAIN_MAX_OUTPUTS];
+    uint8_t out_acc[SL_CHAIN_MAX_OUTPUTS];
+} sl_chain_prog;
+int sl_fused_chain(sl_ctx* ctx, int dtype, const sl_chain_prog* prog, const void* const* inputs, void* const* outputs, size_t n);
+
 /* ---------------------------------------------------------------- G: gemm / trans_gemm */
 
 /* out[m x n] = lhs[m x k] * rhs[k x n]  (SET).  mode < 0 -> ctx default.
