@@ -109,6 +109,45 @@ def unary_grad(op, x, x_grad, out_grad, p0=0.0, p1=0.0):
     s = _chk(x, x_grad, out_grad)
     _fn("orc_unary_grad", s)(_i(op), _d(p0), _d(p1), _p(x), _p(x_grad), _p(out_grad), _sz(x.size))
 
+def unary_deriv(op, x, p0=0.0, p1=0.0):
+    s = _chk(x)
+    out = np.empty_like(x)
+    _fn("orc_unary_deriv", s)(_i(op), _d(p0), _d(p1), _p(x), _p(out), _sz(x.size))
+    return out
+
+
+def chain_replay(listing, inputs, outputs):
+    """Op-by-op replay of a fused-chain program (sliced_b200.chain.Prog.listing()) with the oracle's single-op loops: every
+    instruction is one full pass over the arrays, exactly the launch-per-op sequence the fused kernel replaces.  outputs: arrays
+    updated in place (SET, or ACC when the program says so)."""
+    CH_RDIV_IMM, CH_CONST, CH_COPY, CH_UNARY_F, CH_UNARY_D = 4, 5, 6, 16, 48
+    dt = inputs[0].dtype if inputs else outputs[0].dtype
+    n = outputs[0].size
+    regs = [None] * listing["n_regs"]
+    for r in range(listing["n_in"]):
+        regs[r] = inputs[r].copy()
+    for (op, dst, a, b, p0, p1) in listing["instr"]:
+        if op <= 3:
+            v = binary_ew(op, regs[a], regs[b])
+        elif op == CH_RDIV_IMM:
+            v = binary_ew(DIV, np.full(n, p0, dt), regs[a])
+        elif op == CH_CONST:
+            v = np.full(n, p0, dt)
+        elif op == CH_COPY:
+            v = regs[a].copy()
+        elif op >= CH_UNARY_D:
+            v = unary_deriv(op - CH_UNARY_D, regs[a], p0, p1)
+        else:
+            v = unary(op - CH_UNARY_F, regs[a], p0, p1)
+        regs[dst] = v
+    for j, (r, acc) in enumerate(zip(listing["out_reg"], listing["out_acc"])):
+        if acc:
+            outputs[j][:] = binary_ew(ADD, outputs[j].copy(), regs[r])
+        else:
+            outputs[j][:] = regs[r]
+    return outputs
+
+
 
 # ---------------------------------------------------------------- row_op / col_op
 
