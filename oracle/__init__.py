@@ -116,10 +116,11 @@ def unary_deriv(op, x, p0=0.0, p1=0.0):
     return out
 
 
-def chain_replay(listing, inputs, outputs):
+def chain_replay(listing, inputs, outputs, scale=None):
     """Op-by-op replay of a fused-chain program (sliced_b200.chain.Prog.listing()) with the oracle's single-op loops: every
     instruction is one full pass over the arrays, exactly the launch-per-op sequence the fused kernel replaces.  outputs: arrays
-    updated in place (SET, or ACC when the program says so)."""
+    updated in place (SET, or ACC when the program says so).  scale (optional float64 array, updated in place): element-wise largest
+    magnitude any register held — the yardstick for comparing programs that contain libm calls."""
     CH_RDIV_IMM, CH_CONST, CH_COPY, CH_UNARY_F, CH_UNARY_D = 4, 5, 6, 16, 48
     dt = inputs[0].dtype if inputs else outputs[0].dtype
     n = outputs[0].size
@@ -140,6 +141,8 @@ def chain_replay(listing, inputs, outputs):
         else:
             v = unary(op - CH_UNARY_F, regs[a], p0, p1)
         regs[dst] = v
+        if scale is not None:
+            np.maximum(scale, np.abs(v.astype(np.float64)), out=scale)
     for j, (r, acc) in enumerate(zip(listing["out_reg"], listing["out_acc"])):
         if acc:
             outputs[j][:] = binary_ew(ADD, outputs[j].copy(), regs[r])

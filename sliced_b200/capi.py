@@ -106,6 +106,7 @@ def _declare(lib):
         "sl_col_op": ([_vp, _i, _i, _sz, _sz, _vp, _vp, _vp], _i),
         "sl_col_op_grad": ([_vp, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp, _vp], _i),
         "sl_sgd_step": ([_vp, _i, _vp, _vp, _d, _sz], _i),
+        "sl_fused_chain": ([_vp, _i, _vp, _vp, _vp, _sz], _i),   # (typed prototype: sliced_b200/chain.py)
         "sl_chained_fwd": ([_vp, _i, _vp, _vp, _vp, _sz], _i),
         "sl_chained_bwd": ([_vp, _i, _vp, _vp, _vp, _vp, _vp, _sz], _i),
         "sl_gemm": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _i], _i),

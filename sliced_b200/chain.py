@@ -50,7 +50,7 @@ def _lib():
                                 ("slh_chain_build_backward", [vp, P(i), i, P(i), i, P(Prog)], i)):
             f = getattr(lib, name)
             f.argtypes, f.restype = args, res
-        lib.sl_fused_chain.argtypes = [vp, i, P(Prog), P(vp), P(vp), C.c_size_t]
+        lib.sl_fused_chain.argtypes = [vp, i, P(Prog), P(vp), P(vp), C.c_size_t]   # refines the untyped binding of capi.py
         lib.sl_fused_chain.restype = i
         _declared = True
     return lib

@@ -40,6 +40,10 @@ def _lib():
             "slh_zero_grad": ([_vp], _i),
             "slh_tape_len": ([_vp], _i),
             "slh_n_grads": ([_vp], _i),
+            "slh_set_fusion": ([_vp, _i], _i),
+            "slh_flush": ([_vp], _i),
+            "slh_fused_groups": ([_vp], _i),
+            "slh_unfused_groups": ([_vp], _i),
             "slh_set_tape_enabled": ([_vp, _i], None),
             "slh_set_gemm_mode": ([_vp, _i], _i),
             "slh_buffer_new": ([_vp, _sz, _i], _vp),
@@ -203,6 +207,20 @@ class CUDA:
 
     def tape_len(self) -> int:
         return _lib().slh_tape_len(self.h)
+
+    def set_fusion(self, on: bool = True):
+        """custos `Lazy` + `optimize()` for element-wise chains: binary / unary ops are recorded and run as ONE sl_fused_chain launch
+        when their values are needed (forward), and their grad closures as one fused backward launch."""
+        _chk(_lib().slh_set_fusion(self.h, int(on)))
+        return self
+
+    def flush(self):
+        _chk(_lib().slh_flush(self.h))
+
+    @property
+    def fused_groups(self) -> int: return _lib().slh_fused_groups(self.h)
+    @property
+    def unfused_groups(self) -> int: return _lib().slh_unfused_groups(self.h)
 
     def n_grads(self) -> int:
         """number of live gradient buffers (a buffer's gradient is released with the buffer)"""

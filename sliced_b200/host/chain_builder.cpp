@@ -9,17 +9,20 @@ namespace slh {
 
 int ChainBuilder::input() {
     vals_.push_back(Val{0, n_inputs_, -1, -1, 0, 0});   // op = index among the inputs
+    nograd_.push_back(0);
     ++n_inputs_;
     return (int)vals_.size() - 1;
 }
 
 int ChainBuilder::binary(int binop, int lhs, int rhs) {
     vals_.push_back(Val{1, binop, lhs, rhs, 0, 0});
+    nograd_.push_back(0);
     return (int)vals_.size() - 1;
 }
 
 int ChainBuilder::unary(int unop, int x, double p0, double p1) {
     vals_.push_back(Val{2, unop, x, -1, p0, p1});
+    nograd_.push_back(0);
     return (int)vals_.size() - 1;
 }
 
@@ -59,7 +62,8 @@ bool ChainBuilder::build_forward(const std::vector<int>& outs, sl_chain_prog* pr
     return allocate(s, prog, why);
 }
 
-bool ChainBuilder::build_backward(const std::vector<int>& seeds, const std::vector<int>& wrt, sl_chain_prog* prog, std::string* why) const {
+bool ChainBuilder::build_backward(const std::vector<int>& seeds, const std::vector<int>& wrt, sl_chain_prog* prog, std::string* why,
+                                  std::vector<int>* seed_totals) const {
     const int S = (int)seeds.size(), W = (int)wrt.size();
     if (S < 1) { if (why) *why = "no seed"; return false; }
     if (W < 1 || W > SL_CHAIN_MAX_OUTPUTS) { if (why) *why = "1..4 gradients"; return false; }
@@ -91,7 +95,7 @@ bool ChainBuilder::build_backward(const std::vector<int>& seeds, const std::vect
     // the ssa ids of forward values refer to LEAF inputs 0..n_inputs_-1, exactly as in the forward program
     for (int v = (int)vals_.size() - 1; v >= 0; --v) {
         const Val& x = vals_[v];
-        if (x.kind == 0 || grad[v] < 0) continue;
+        if (x.kind == 0 || grad[v] < 0 || nograd_[v]) continue;
         const int g = grad[v];
         if (x.kind == 1) {
             const bool wl = wanted[x.a], wr = wanted[x.b];
@@ -133,6 +137,7 @@ bool ChainBuilder::build_backward(const std::vector<int>& seeds, const std::vect
         if (got_internal[seeds[i]]) {
             if ((int)s.outs.size() >= SL_CHAIN_MAX_OUTPUTS) { if (why) *why = "too many gradient outputs"; return false; }
             s.outs.push_back(grad[seeds[i]]);
+            if (seed_totals) seed_totals->push_back(i);
         }
     return allocate(s, prog, why);
 }
@@ -211,6 +216,7 @@ void slh_chain_free(slh_chain* c) { delete (slh::ChainBuilder*)c; }
 int slh_chain_input(slh_chain* c) { return ((slh::ChainBuilder*)c)->input(); }
 int slh_chain_binary(slh_chain* c, int binop, int lhs, int rhs) { return ((slh::ChainBuilder*)c)->binary(binop, lhs, rhs); }
 int slh_chain_unary(slh_chain* c, int unop, int x, double p0, double p1) { return ((slh::ChainBuilder*)c)->unary(unop, x, p0, p1); }
+void slh_chain_no_grad(slh_chain* c, int v) { ((slh::ChainBuilder*)c)->no_grad(v); }
 int slh_chain_build_forward(slh_chain* c, const int* outs, int n_outs, sl_chain_prog* prog) {
     return ((slh::ChainBuilder*)c)->build_forward(std::vector<int>(outs, outs + n_outs), prog, nullptr) ? 0 : -1;
 }

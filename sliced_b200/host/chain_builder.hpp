@@ -28,6 +28,7 @@ class ChainBuilder {
     int input();
     int binary(int binop, int lhs, int rhs);                     // SL_ADD / SL_SUB / SL_MUL / SL_DIV
     int unary(int unop, int x, double p0 = 0, double p1 = 0);     // sl_unop forward function
+    void no_grad(int v) { nograd_[v] = 1; }                       // a node whose op registers no grad closure (apply_fn, clip, div)
     int n_values() const { return (int)vals_.size(); }
     int n_inputs() const { return n_inputs_; }
     int n_nodes() const { return (int)vals_.size() - n_inputs_; }
@@ -42,7 +43,9 @@ class ChainBuilder {
     // place: output j = wrt[j], SET of old + contributions in tape order) | then, when write_seed_totals, nothing more: a seed
     // that is itself consumed inside the chain accumulates those contributions too, and every seed's total is what flows on.
     // n_inputs() + seeds.size() + wrt.size() must be <= SL_CHAIN_MAX_INPUTS and wrt.size() <= SL_CHAIN_MAX_OUTPUTS.
-    bool build_backward(const std::vector<int>& seeds, const std::vector<int>& wrt, sl_chain_prog* prog, std::string* why) const;
+    // seed_totals (optional): indices into `seeds` of the seeds that got such an extra output, in output order.
+    bool build_backward(const std::vector<int>& seeds, const std::vector<int>& wrt, sl_chain_prog* prog, std::string* why,
+                        std::vector<int>* seed_totals = nullptr) const;
 
   private:
     struct Val {
@@ -52,6 +55,7 @@ class ChainBuilder {
         double p0, p1;
     };
     std::vector<Val> vals_;
+    std::vector<char> nograd_;
     int n_inputs_ = 0;
 
     // straight-line SSA produced by the builders before register allocation

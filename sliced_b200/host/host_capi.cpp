@@ -47,6 +47,10 @@ void slh_range_begin(slh_device* d) { ((Device*)d)->range_begin(); }
 int slh_zero_grad(slh_device* d) { return guard([&]() { ((Device*)d)->zero_grad(); return 0; }, -1); }
 int slh_tape_len(slh_device* d) { return (int)((Device*)d)->tape_len(); }
 int slh_n_grads(slh_device* d) { return (int)((Device*)d)->n_grads(); }
+int slh_set_fusion(slh_device* d, int on) { return guard([&]() { ((Device*)d)->set_fusion(on != 0); return 0; }, -1); }
+int slh_flush(slh_device* d) { return guard([&]() { ((Device*)d)->flush_pending(); return 0; }, -1); }
+int slh_fused_groups(slh_device* d) { return (int)((Device*)d)->fused_groups(); }
+int slh_unfused_groups(slh_device* d) { return (int)((Device*)d)->unfused_groups(); }
 void slh_set_tape_enabled(slh_device* d, int on) { ((Device*)d)->set_tape_enabled(on != 0); }
 int slh_set_gemm_mode(slh_device* d, int mode) { return guard([&]() { ((Device*)d)->set_gemm_mode(mode); return 0; }, -1); }
 

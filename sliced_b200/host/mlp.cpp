@@ -94,6 +94,7 @@ StepResult Mlp::forward_backward(const Buf& x, const Buf& y, const Buf& labels, 
         else if (loss_ == LOSS_SOFTMAX_CCE) out = out.softmax();
     }
     const size_t on = batch * out_cols;
+    d.flush_pending();   // (fusion: the raw device pointers used below must hold their values)
     d.check(sl_clear(d.ctx(), metrics_dev_, 16));
     if (loss_ == LOSS_SOFTMAX_CCE) {
         if (labels)  // accuracy: nn.rs:195-211 (a host loop in the reference; a kernel + one int here)
@@ -107,12 +108,14 @@ StepResult Mlp::forward_backward(const Buf& x, const Buf& y, const Buf& labels, 
         // cce_grad(preds, targets, rows): nn.rs:140-152
         Buf grad = d.binary_ew(SL_DIV, y, out.data);
         grad = d.apply_fn(grad, SL_UN_NEG_DIV_SCALAR, (double)grad_rows);
+        d.flush_pending();
         d.set_tape_enabled(true);
         d.check(sl_sum(d.ctx(), SL_F32, loss->dptr, batch, metrics_dev_));   // device.mean(&loss) * batch (nn.rs:224)
         d.backward_with(out.data, grad);                                      // nn.rs:233
     } else {
         Matrix ym(y, batch, out_cols);
         Matrix loss = out.sub(ym).pow(2.);                                    // sine_net.rs:150
+        d.flush_pending();
         d.check(sl_sum(d.ctx(), SL_F32, loss.data->dptr, on, metrics_dev_));  // dev.mean(&loss) * len (sine_net.rs:151)
         d.backward(loss.data);                                                // sine_net.rs:156
     }

@@ -39,6 +39,8 @@ struct BufferImpl {
     void* dptr = nullptr;
     bool requires_grad = true;  // custos buffers take part in autograd unless `.no_grad()` (examples/nn.rs:170,177)
     bool owns = true;
+    bool pending = false;       // fusion: recorded in an open element-wise chain, not computed yet (dptr may still be null)
+    std::shared_ptr<BufferImpl> backing;   // fusion: the (cached) allocation a materialised chain output lives in
     Device* dev = nullptr;
     ~BufferImpl();
     size_t bytes() const { return len * (dtype == SL_F64 ? 8 : 4); }
@@ -83,6 +85,16 @@ class Device {
     void set_tape_enabled(bool on) { tape_enabled_ = on; }
     void set_gemm_mode(int mode) { check(sl_ctx_set_gemm_mode(ctx_, mode)); }
 
+    // ---- custos `Lazy` + `optimize()` analogue for element-wise chains (examples/chained_perf.rs:114, sine_net.rs:178-233): with
+    // fusion on, binary / unary element-wise ops are RECORDED instead of launched; the chain runs as one sl_fused_chain launch when
+    // something needs its values (any other op, read, backward), materialising only the results somebody still holds a handle to, and
+    // its grad closures become one fused backward launch.  Chains that do not fit the interpreter run op by op as before.
+    void set_fusion(bool on) { flush_pending(); fusion_ = on; }
+    bool fusion() const { return fusion_; }
+    void flush_pending();
+    size_t fused_groups() const { return fused_groups_; }       // chains executed as one launch so far
+    size_t unfused_groups() const { return unfused_groups_; }   // recorded chains that had to run op by op
+
     // ---- L3: src/ops.rs
     Buf add(const Buf& lhs, const Buf& rhs);                        // BinaryOpsMayGrad::add   ops.rs:115-132
     Buf add2(const Buf& lhs, const Buf& rhs);                       // BinaryOpsMayGrad::add2  ops.rs:173-186
@@ -90,6 +102,7 @@ class Device {
     Buf mul(const Buf& lhs, const Buf& rhs);                        // ops.rs:153-171
     Buf div(const Buf& lhs, const Buf& rhs);                        // BinaryElementWise::div (no grad in the reference; binary_ew/mod.rs:85-90)
     Buf binary_ew(int binop, const Buf& lhs, const Buf& rhs);       // L2 BinaryElementWise::{add,sub,mul,div}: forward only, nothing on the tape
+    Buf record_binary(int binop, const Buf& lhs, const Buf& rhs, bool with_grad, bool add2);  // (shared body of the five above)
     Buf square(const Buf& x);                                       // SquareMayGrad ops.rs:25-45
     Buf pow(const Buf& x, double rhs);                              // PowMayGrad    ops.rs:64-77
     Buf transpose(size_t rows, size_t cols, const Buf& x);          // TransposeMayGrad ops.rs:207-220
@@ -119,6 +132,18 @@ class Device {
     void sgd_step(const Buf& param, double lr);                     // SGD::step examples/nn.rs:108-119 (param -= grad * lr)
 
   private:
+    struct FNode {   // one recorded element-wise op
+        int kind;    // 1 binary (sl_binop), 2 unary (sl_unop)
+        int op;
+        Buf a, b, dst;
+        double p0, p1;
+        bool with_grad, add2;
+    };
+    Buf record(FNode n);
+    void run_node_unfused(const FNode& n);
+    bool fusion_ = false;
+    std::vector<FNode> pending_;
+    size_t fused_groups_ = 0, unfused_groups_ = 0;
     Buf new_buffer(size_t len, int dtype, bool zero);
     double scalar_out(int (*fn)(sl_ctx*, int, const void*, size_t, void*), const Buf& x);
 

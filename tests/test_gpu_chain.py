@@ -57,11 +57,13 @@ def test_random_programs_match_oracle_replay(ctx, seed, n):
             d_out = [ctx.array(rng.uniform(-9, 9, n).astype(dt)) for _ in range(n_out)]   # junk: SET
             h_out = [np.zeros(n, dt) for _ in range(n_out)]
         CH.run(ctx, prog, d_in, d_out, n)
-        O.chain_replay(L, ins, h_out)
+        scale = np.ones(n)
+        O.chain_replay(L, ins, h_out, scale)
         for j, (d, h) in enumerate(zip(d_out, h_out)):
             got = d.numpy()
-            if libm:
-                assert np.all(np.abs(got - h) <= 2e-6 * np.maximum(np.abs(h), 1e-3) if dt == np.float32 else np.abs(got - h) <= 1e-12 * np.maximum(np.abs(h), 1e-3)), (seed, j)
+            if libm:   # CUDA libm vs glibc differ in the last ulps; later instructions amplify that by at most the register magnitudes
+                tol = (2e-5 if dt == np.float32 else 1e-12) * np.maximum(scale, np.abs(h))
+                assert np.all(np.abs(got.astype(np.float64) - h) <= tol), (seed, j, np.max(np.abs(got - h) / tol))
             else:
                 assert bits_equal(got, h), (seed, n, j, np.max(np.abs(got - h)))
 
