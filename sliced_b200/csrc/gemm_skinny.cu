@@ -162,6 +162,56 @@ __global__ void __launch_bounds__(256) skinny_fold_kernel(size_t total, size_t n
     }
 }
 
+// ------------------------------------------------------------------------------------------------ tn, small output, deep K
+// C[m x n] (+)= A[k x m]^T * B[k x n] with few 64 x 64 output tiles and a long contraction: the weight gradients of small layers
+// (examples/sine_net.rs: 64 x 64, 1 x 64 and 64 x 1 outputs over K = 1000 samples).  The generic CUDA-core kernel gives such a
+// problem ONE block walking all of K (71 us per launch measured: 53 % of a sine_net step); here K is split over
+// gridDim.z blocks (deterministic partials + fold), both operands are read coalesced (k is the slow index of both), and each
+// thread keeps a 4 x 4 block of outputs in registers.
+template <bool DIRECT_ACC>
+__global__ void __launch_bounds__(256) smallout_tn_kernel(size_t m, size_t n, size_t k, size_t kps, const float* __restrict__ A,
+                                                          const float* __restrict__ B, float* out, int direct) {
+    constexpr int KT = 32;
+    __shared__ float As[KT][64 + 4], Bs[KT][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const size_t m0 = (size_t)blockIdx.y * 64, n0 = (size_t)blockIdx.x * 64;
+    const size_t k0 = (size_t)blockIdx.z * kps, k1 = k0 + kps < k ? k0 + kps : k;
+    float acc[4][4] = {};
+    for (size_t kb = k0; kb < k1; kb += KT) {
+#pragma unroll
+        for (int i = 0; i < (KT * 64) / 256; ++i) {
+            const int e = threadIdx.x + i * 256;
+            const int kk = e >> 6, c = e & 63;
+            const size_t kr = kb + kk;
+            As[kk][c] = (kr < k1 && m0 + c < m) ? __ldg(A + kr * m + m0 + c) : 0.f;
+            Bs[kk][c] = (kr < k1 && n0 + c < n) ? __ldg(B + kr * n + n0 + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < KT; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* dst = direct ? out : out + (size_t)blockIdx.z * m * n;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const size_t r = m0 + ty * 4 + i;
+        if (r >= m) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const size_t c = n0 + tx * 4 + j;
+            if (c < n) dst[r * n + c] = (DIRECT_ACC ? dst[r * n + c] : 0.f) + acc[i][j];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ nt
 // Thread owns 4 consecutive output columns: their B rows (4 x KP) live in registers for the whole kernel.  A CTA covers
 // 1024 columns and a slab of rows whose A values ([rows x KP], padded to KP + 2) are staged in shared memory and read as
@@ -276,6 +326,32 @@ int sl_gemm_skinny_f32(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n
         if (accumulate) SL_LAUNCH(ctx, (skinny_fold_kernel<true>), fgrid, 256, 0, total, nsplit, (const float*)ws, c);
         else SL_LAUNCH(ctx, (skinny_fold_kernel<false>), fgrid, 256, 0, total, nsplit, (const float*)ws, c);
         return SL_OK;
+    }
+    if (trans_a && !trans_b && k >= 256) {   // few output tiles, deep K: split K over the SMs (see smallout_tn_kernel)
+        const size_t gx = (n + 63) / 64, gy = (m + 63) / 64, tiles = gx * gy;
+        if (tiles <= (size_t)ctx->num_sms / 2 && gx <= 65535 && gy <= 65535) {
+            size_t nsplit = ((size_t)ctx->num_sms * 2) / tiles;
+            const size_t max_split = (k + 63) / 64;
+            nsplit = nsplit > max_split ? max_split : (nsplit < 1 ? 1 : nsplit);
+            size_t kps = (k + nsplit - 1) / nsplit;
+            kps = (kps + 31) & ~size_t(31);
+            nsplit = (k + kps - 1) / kps;
+            const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)nsplit);
+            if (nsplit == 1) {
+                if (accumulate) SL_LAUNCH(ctx, (smallout_tn_kernel<true>), grid, 256, 0, m, n, k, kps, a, b, c, 1);
+                else SL_LAUNCH(ctx, (smallout_tn_kernel<false>), grid, 256, 0, m, n, k, kps, a, b, c, 1);
+                return SL_OK;
+            }
+            void* ws = nullptr;
+            int rc = sl_ws_reserve(ctx, nsplit * m * n * sizeof(float), &ws);
+            if (rc != SL_OK) return rc;
+            SL_LAUNCH(ctx, (smallout_tn_kernel<false>), grid, 256, 0, m, n, k, kps, a, b, (float*)ws, 0);
+            const size_t total = m * n, cap = (size_t)ctx->num_sms * 8, fb = (total + 255) / 256;
+            const unsigned fgrid = (unsigned)(fb < cap ? fb : cap);
+            if (accumulate) SL_LAUNCH(ctx, (skinny_fold_kernel<true>), fgrid, 256, 0, total, nsplit, (const float*)ws, c);
+            else SL_LAUNCH(ctx, (skinny_fold_kernel<false>), fgrid, 256, 0, total, nsplit, (const float*)ws, c);
+            return SL_OK;
+        }
     }
     if (!trans_a && trans_b && k >= 1 && k <= 16 && n >= 64 && m >= 64 && n % 4 == 0 && al && (!mask_src || sl_aligned16(mask_src))) {
         const int kp = (int)((k + 1) & ~size_t(1));

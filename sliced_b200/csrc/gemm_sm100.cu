@@ -1679,7 +1679,11 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
     if (mode < 0) mode = ctx->gemm_mode;
     // a gemm that overwrites a buffer whose planes are cached makes them stale
     sl_note_writes(ctx, c, epi.c2);
-    if (dtype != SL_F32 || mode == SL_GEMM_SIMT || !tc_eligible(m, n, k)) {
+    // a few output tiles over a deep contraction (weight gradients of small layers): one tensor-core tile per SM would leave the
+    // machine idle; the split-K CUDA-core kernel (gemm_skinny.cu smallout_tn_kernel) spreads K over all SMs instead
+    const bool small_tn = dtype == SL_F32 && trans_a && !trans_b && k >= 256 && ((m + 63) / 64) * ((n + 63) / 64) <= (size_t)ctx->num_sms / 2 &&
+                          !env_int("SLICED_GEMM_TC_FORCE", 0);
+    if (dtype != SL_F32 || mode == SL_GEMM_SIMT || !tc_eligible(m, n, k) || small_tn) {
         if (epi.any() && dtype != SL_F32) return sl_set_error(ctx, SL_ERR_UNSUPPORTED, "fused epilogue is f32 only");
         int rc = 1;
         int mask_done = 0;

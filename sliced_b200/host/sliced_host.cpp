@@ -292,11 +292,15 @@ void Device::flush_pending() {
     add_grad_fn([this, group]() {
         std::vector<int> seeds, wrt;
         std::vector<Buf> seed_grads, wrt_grads;
-        for (size_t k = 0; k < group->live.size(); ++k)
-            if (has_grad(group->live[k])) {
-                seeds.push_back(group->live_value[k]);
-                seed_grads.push_back(grad(group->live[k]));
-            }
+        bool any_seed = false;
+        for (size_t k = 0; k < group->live.size(); ++k) any_seed = any_seed || has_grad(group->live[k]);
+        if (!any_seed) return;   // no gradient reaches this chain
+        // every materialised result is a seed: one that nothing outside contributed to starts from zeros, and still receives (and
+        // shows through `.grad()`) what the chain's own later ops contribute — as its buffer would in the reference
+        for (size_t k = 0; k < group->live.size(); ++k) {
+            seeds.push_back(group->live_value[k]);
+            seed_grads.push_back(grad(group->live[k]));
+        }
         for (size_t k = 0; k < group->leaves.size(); ++k)
             if (group->leaves[k]->requires_grad) {
                 wrt.push_back(group->leaf_value[k]);

@@ -58,7 +58,10 @@ def test_chained_perf_graph_is_13_instructions_in_6_registers():
     from sliced_b200.chain import Chain
     ch = Chain()
     x, b = ch.inputs(2)
-    out = x.square() * x + (b + x) * b
+    squared = x.square()                 # registration order of chained_perf.rs:86-90 (the tape replays it in reverse)
+    add = b + x
+    mul_b = add * b
+    out = squared * x + mul_b
     fwd, bwd = ch.forward([out]), ch.backward([out], [x, b])
     assert (fwd.n_instr, fwd.n_regs, fwd.n_in, fwd.n_out) == (5, 3, 2, 1)
     assert (bwd.n_instr, bwd.n_in, bwd.n_out) == (13, 5, 2) and bwd.n_regs <= 6

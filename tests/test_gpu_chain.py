@@ -73,7 +73,10 @@ def test_chained_perf_programs_equal_the_hand_fused_kernels(ctx):
     from sliced_b200 import chain as CH
     ch = CH.Chain()
     x, b = ch.inputs(2)
-    out = x.square() * x + (b + x) * b
+    squared = x.square()                 # registration order of chained_perf.rs:86-90 (the tape replays it in reverse)
+    add = b + x
+    mul_b = add * b
+    out = squared * x + mul_b
     fwd, bwd = ch.forward([out]), ch.backward([out], [x, b])
     rng = np.random.default_rng(4)
     for n in (7, 1 << 20, (1 << 20) + 3):

@@ -25,7 +25,10 @@ def test_chained_perf_graph_fused_vs_unfused():
     for dev in (plain, fused):
         x, b = dev.buffer(xs), dev.buffer(bs)
         l0 = dev.launches
-        out = dev.add(dev.mul(dev.square(x), x), dev.mul(dev.add(b, x), b))   # intermediates are dropped as soon as they are consumed
+        # registration order of chained_perf.rs:86-90; intermediates are dropped as soon as they are consumed
+        mul_b = dev.mul(dev.add(b, x), b)
+        out = dev.add(dev.mul(dev.square(x), x), mul_b)
+        del mul_b
         o = out.read()
         l1 = dev.launches
         out.backward()
@@ -51,16 +54,15 @@ def test_live_intermediates_no_grad_leaves_and_gradless_ops(cached):
     for dev in (plain, fused):
         x, y, z = dev.buffer(xs), dev.buffer(ys), dev.buffer(zs).no_grad()
         sq = dev.square(x)                       # a handle is kept: must be materialised, and its gradient must be complete
-        t = dev.mul(sq, y)
-        c = dev.clip(t, 0.5, 1.5)                # Clip registers no grad closure (ops.rs:419-425): nothing flows through it
-        out = dev.add(dev.sub(t, z), dev.mul(c, sq))
+        # Clip registers no grad closure (ops.rs:419-425): nothing flows through it.  Two materialised results (sq, out), three leaves.
+        out = dev.add(dev.sub(dev.mul(sq, y), z), dev.mul(dev.clip(dev.mul(sq, y), 0.5, 1.5), sq))
         o, s = out.read(), sq.read()
         out.backward()
         res.append((o, s, x.grad().read(), y.grad().read(), sq.grad().read()))
         assert dev.n_grads() >= 3
     for a, b in zip(*res):
         assert np.array_equal(a, b)
-    assert fused.fused_groups >= 1
+    assert fused.fused_groups >= 1 and fused.unfused_groups == 0
     plain.close(); fused.close()
 
 

@@ -334,7 +334,10 @@ def test_full_size_sampled(ctx, mode):
                                   # odd small extents (zero-padded column), B too large for shared memory (v1 fallback), ragged row tails
                                   ("NN", 0, 0, 1001, 7, 512), ("NN", 0, 0, 300, 16, 16384), ("NN", 0, 0, 8200, 10, 4096),
                                   ("TN", 1, 0, 1028, 7, 5000), ("TN", 1, 0, 4096, 10, 65536), ("NT", 0, 1, 777, 1028, 9),
-                                  ("NT", 0, 1, 5000, 4096, 10)],
+                                  ("NT", 0, 1, 5000, 4096, 10),
+                                  # few output tiles over a deep contraction (sine_net's weight gradients): split-K CUDA-core kernel
+                                  ("TN", 1, 0, 64, 64, 1000), ("TN", 1, 0, 1, 64, 1000), ("TN", 1, 0, 64, 1, 1000), ("TN", 1, 0, 200, 130, 5000),
+                                  ("TN", 1, 0, 64, 64, 65536), ("TN", 1, 0, 67, 129, 300)],
                          ids=lambda c: f"{c[0]}-{c[3]}x{c[4]}x{c[5]}")
 def test_skinny_shapes(case, monkeypatch):
     """the HBM-bound skinny kernels (the 10-class head of the nn.rs MLP): fp32 FMA accumulation, K-scaled tolerance"""
