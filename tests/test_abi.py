@@ -97,3 +97,10 @@ def test_rust_patch_uses_only_declared_symbols():
                 assert (commas + 1 if any_arg else 0) == arity[name], f"{f}: {name} called with {commas + 1} args, header has {arity[name]}"
                 used += 1
     assert used >= 20
+    # one authored `cuda.rs` per device trait family of SURVEY 8(b), plus the custos apply_fn / add_unary_grad shim
+    want = ["binary_ew/cuda.rs", "gemm/cuda.rs", "gemm/grad/cuda.rs", "row_op/cuda.rs", "row_op/grad/cuda.rs", "col_op/cuda.rs", "col_op/grad/cuda.rs",
+            "max/cuda.rs", "sum/cuda.rs", "mean/cuda.rs", "mean/grad/cuda.rs", "transpose/cuda.rs", "softmax/cuda.rs", "diagflat/cuda.rs",
+            "diagflat/grad/cuda.rs", "onehot/cuda.rs", "onehot/grad/cuda.rs"]
+    for w in want:
+        assert os.path.exists(os.path.join(patch, "ops2", w)), f"reference-patch is missing src/ops2/{w}"
+    assert os.path.exists(os.path.join(patch, "custos_shim", "apply_fn.rs"))
