@@ -218,6 +218,7 @@ struct GemmParams {
     int kc_first;           // 2-CTA kernel: k-blocks of the FIRST TWO chunks of every tile (>= kc_blocks; see the kernel)
     int debug;              // bit 0: skip the final store (timing experiments only, SLICED_GEMM_DEBUG)
     unsigned long long hint_a, hint_b;   // L2 eviction-priority policy of the A / B operand loads (0 = none)
+    int dynamic;            // 2-CTA kernel: 1 = one cluster per work unit, units handed out by cluster launch control (work stealing)
 };
 
 // shared epilogue arithmetic of both MMA kernels: 4 consecutive columns of one output row
@@ -559,6 +560,29 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
                  : "memory");
 }
 
+// ---- dynamic work distribution: cluster launch control (Blackwell's hardware work-stealing).  The grid has one cluster per work
+// unit; a running cluster asks the launcher to CANCEL a not-yet-launched cluster and takes over its unit.  The 16-byte response is
+// multicast to the same shared-memory offset of both CTAs of the pair and completes a transaction barrier in each.
+__device__ __forceinline__ void clc_try_cancel_2sm(uint32_t resp_addr, uint32_t bar) {
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+                 ::"r"(resp_addr), "r"(bar) : "memory");
+}
+// blockIdx.x of the first CTA of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_response_ctaid_x(uint32_t resp_addr) {
+    uint32_t x, valid;
+    asm volatile(
+        "{\n\t.reg .pred p1;\n\t.reg .b128 resp;\n\t"
+        "ld.shared.b128 resp, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, resp;\n\t"
+        "selp.u32 %1, 1, 0, p1;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, resp;\n\t}"
+        : "=r"(x), "=r"(valid)
+        : "r"(resp_addr)
+        : "memory");
+    return valid ? (int)x : -1;
+}
+
 // ---- coalesced epilogue.  tcgen05.ld hands every thread one accumulator ROW, so storing straight from registers makes each
 // warp-wide STG touch 32 different rows = 32 cache lines (measured: the store phase, not the MMAs, bounded the K = 4096 gemms at
 // 75 % tensor-pipe activity).  Instead each warp bounces 32 x 32 blocks through a private 4 KB shared-memory tile (16-byte chunks
@@ -639,6 +663,14 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    // dynamic scheduling (p.dynamic): a ring of SCHED_SLOTS launch-control responses, one full barrier per CTA (16 response bytes),
+    // one empty barrier in the leader (every consumer of both CTAs: 2 producers, 1 MMA thread, 2 x 8 epilogue warps)
+    constexpr int SCHED_SLOTS = 2;
+    constexpr uint32_t SCHED_CONSUMERS = 2 * (1 + EPI_WARPS) + 1;
+    auto sched_full_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + 6 + s); };
+    auto sched_empty_bar = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + 6 + SCHED_SLOTS + s); };
+    auto sched_resp = [&](uint32_t s) { return bar_base + 8u * (2 * STAGES + 6 + 2 * SCHED_SLOTS) + 16u * s; };
+    static_assert(8 * (2 * STAGES + 6 + 2 * SCHED_SLOTS) + 16 * SCHED_SLOTS <= 256, "barrier area is 256 bytes");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -664,6 +696,10 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         for (int s = 0; s < 2; ++s) {
             mbar_init(tmem_full_bar(s), 1);
             mbar_init(tmem_empty_bar(s), 2 * EPI_WARPS);  // both CTAs' epilogue warps; only the leader's copy is used
+        }
+        for (int s = 0; s < SCHED_SLOTS; ++s) {
+            mbar_init(sched_full_bar(s), 1);                 // this CTA's producer arms it (+ 16 response bytes)
+            mbar_init(sched_empty_bar(s), SCHED_CONSUMERS);  // only the leader's copy is used
         }
         fence_barrier_init();
         fence_proxy_async();
@@ -694,6 +730,33 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     const int num_units = num_tiles * splits;
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
+    // Unit sequence of this cluster.  Static: cluster_id, + num_clusters, ... (persistent grid of one cluster per SM pair).
+    // Dynamic: the grid holds one cluster per unit; a cluster starts with its own unit and then takes over the units of clusters
+    // that have not been launched yet (clusterlaunchcontrol.try_cancel) until none is left.  SMs held by another kernel (the NCCL
+    // exchange of a data-parallel step) then just mean fewer clusters sharing the same queue, instead of whole static shares of
+    // the tiles waiting for those SMs.  Fetch number i (issued by the leader's producer when it STARTS its i-th unit, so the
+    // round trip hides behind that unit) names the (i+1)-th unit; every role of both CTAs reads it when it finishes its i-th.
+    const bool dyn = p.dynamic != 0;
+    auto sched_prefetch = [&](uint32_t it) {   // producer threads of both CTAs
+        const uint32_t slot = it % SCHED_SLOTS;
+        if (leader) mbar_wait(sched_empty_bar(slot), ((it / SCHED_SLOTS) & 1) ^ 1);   // everybody has read fetch it - SCHED_SLOTS
+        mbar_expect_tx(sched_full_bar(slot), 16);
+        if (leader) clc_try_cancel_2sm(sched_resp(slot), sched_full_bar(slot));
+    };
+    auto next_unit = [&](int unit, uint32_t& it, bool whole_warp) -> int {
+        if (!dyn) {
+            const int n = unit + num_clusters;
+            return n < num_units ? n : -1;
+        }
+        const uint32_t slot = it % SCHED_SLOTS, par = (it / SCHED_SLOTS) & 1;
+        ++it;
+        mbar_wait(sched_full_bar(slot), par);
+        const int x = clc_response_ctaid_x(sched_resp(slot));
+        fence_proxy_async();   // this (generic-proxy) read is ordered before the next (async-proxy) response written to the slot
+        if (whole_warp) __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(sched_empty_bar(slot), 0));
+        return x < 0 ? -1 : (x >> 1);
+    };
     auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
         // grouped raster: `grp` blocks of the grouped dimension stay L2-resident while the other dimension is swept
         if (p.group_along_n) {
@@ -720,7 +783,9 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+            uint32_t it = 0;
+            for (int unit = cluster_id; unit >= 0; unit = next_unit(unit, it, false)) {
+                if (dyn) sched_prefetch(it);
                 int m_blk, n_blk;
                 tile_coords(unit / splits, m_blk, n_blk);
                 const int kb0 = (unit % splits) * kbs, kb1 = min(num_kb, kb0 + kbs);
@@ -770,7 +835,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             int stage = 0;
             uint32_t phase = 0;
             uint32_t g = 0;
-            for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+            uint32_t it = 0;
+            for (int unit = cluster_id; unit >= 0; unit = next_unit(unit, it, false)) {
                 const int kb0 = (unit % splits) * kbs, kb1 = min(num_kb, kb0 + kbs);
                 const int num_chunks = chunk_count(kb1 - kb0);
                 for (int ch = 0; ch < num_chunks; ++ch, ++g) {
@@ -821,7 +887,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         const int quad = warp & 3;
         const int col0 = (ew >> 2) * CPW;
         uint32_t g = 0;
-        for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        uint32_t it = 0;
+        for (int unit = cluster_id; unit >= 0; unit = next_unit(unit, it, true)) {
             int m_blk, n_blk;
             tile_coords(unit / splits, m_blk, n_blk);
             const int split = unit % splits;
@@ -1291,7 +1358,8 @@ static int launch_cfg_2cta(sl_ctx* ctx, const GemmParams& p, const void* a_hi, c
     // CTAs own all of an SM's shared memory, so an NCCL kernel cannot co-reside with them
     const int reserve = ctx->nccl_comm ? env_int("SLICED_GEMM_RESERVE_SMS", 0) : 0;
     const int max_clusters = (ctx->num_sms - (reserve > 0 && reserve < ctx->num_sms - 2 ? reserve : 0)) / 2;
-    const int grid = 2 * (num_tiles < max_clusters ? num_tiles : max_clusters);
+    // dynamic scheduling: one cluster per work unit, handed out by cluster launch control (see the kernel)
+    const int grid = p.dynamic ? 2 * num_tiles * (p.splits > 0 ? p.splits : 1) : 2 * (num_tiles < max_clusters ? num_tiles : max_clusters);
     sl_ctx::ProfRec rec{};
     if (ctx->profiling) {
         cudaEventCreate(&rec.a);
@@ -1353,6 +1421,7 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
     p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu; p.C2 = c2; p.mask_src = mask_src;
     p.row_scale = row_scale; p.col_scale = col_scale;
     p.debug = env_int("SLICED_GEMM_DEBUG", 0);
+    p.dynamic = env_int("SLICED_GEMM_SCHED", 1) != 0;   // 0: static persistent schedule | 1 (default): cluster launch control
     // L2 residency: when one operand is much smaller than the other (weights vs a batch of activations) and fits in a fraction of
     // L2, its loads are marked evict_last and the big, streamed operand's loads evict_first, so the stream does not flush it.
     p.hint_a = p.hint_b = 0;
