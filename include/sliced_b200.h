@@ -375,6 +375,18 @@ int sl_softmax_grad(sl_ctx* ctx, int dtype, size_t samples, size_t features, voi
 int sl_softmax_cce(sl_ctx* ctx, int dtype, size_t samples, size_t features, const void* logits, const void* targets, const int32_t* labels,
                    size_t grad_rows, void* probs_out, void* logits_grad, void* loss_per_sample, int32_t* correct_dev);
 
+/* The WHOLE training step of a small squared-error MLP — forward, loss, backward, SGD — in one launch of one 16-CTA cluster (8 below 256 samples)
+ * (weights, activations and partial gradients in shared memory; gradients summed over distributed shared memory in rank order):
+ *   a_l = relu(a_{l-1} W_l + b_l) on hidden layers, out = a_{L-1} W_L + b_L          ref: examples/sine_net.rs:135-147 (Linear + relu)
+ *   *loss_sum_dev = sum (out - y)^2 ; tape seed 1 -> d out = 2 (out - y)             ref: examples/sine_net.rs:150-156
+ *   grads = parameter gradients of that tape (SET), params -= grads * lr             ref: examples/sine_net.rs:108-116,158-160
+ * params / grads are flat: layer l's W [dims[l] x dims[l+1]] at float offset seg_off[2l], its bias at seg_off[2l+1].
+ * 1..4 layers of width <= 64, any batch, f32; sl_mlp_small_fits tells whether a shape is taken (SL_ERR_UNSUPPORTED otherwise).
+ * Same arithmetic per element as the op-by-op tape, different (fixed) summation order: K-scaled tolerance against it. */
+int sl_mlp_small_fits(sl_ctx* ctx, int n_layers, const size_t* dims, size_t batch);
+int sl_mlp_small_step(sl_ctx* ctx, int dtype, int n_layers, const size_t* dims, const size_t* seg_off, size_t batch, const void* x,
+                      const void* y, void* params, void* grads, double lr, void* loss_sum_dev);
+
 /* ---------------------------------------------------------------- next-row ops */
 
 /* out[i*n + i] = x[i] (only the diagonal is written).  ref: src/ops2/diagflat/cpu.rs:42-46 */

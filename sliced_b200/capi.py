@@ -140,6 +140,8 @@ def _declare(lib):
         "sl_softmax": ([_vp, _i, _sz, _sz, _vp, _vp], _i),
         "sl_softmax_grad": ([_vp, _i, _sz, _sz, _vp, _vp, _vp], _i),
         "sl_softmax_cce": ([_vp, _i, _sz, _sz, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp], _i),
+        "sl_mlp_small_fits": ([_vp, _i, _vp, _sz], _i),
+        "sl_mlp_small_step": ([_vp, _i, _i, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _d, _vp], _i),
         "sl_diagflat": ([_vp, _i, _sz, _vp, _vp], _i),
         "sl_diagflat_grad": ([_vp, _i, _sz, _vp, _vp], _i),
         "sl_onehot": ([_vp, _i, _sz, _sz, _vp, _vp], _i),

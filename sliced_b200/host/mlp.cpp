@@ -40,6 +40,19 @@ Mlp::Mlp(Device& dev, const std::vector<size_t>& dims, LossKind loss) : dev_(dev
         layers_.push_back(Linear{Matrix(w, I, O), Matrix(b, 1, O)});
     }
     dev_.check(sl_malloc(dev_.ctx(), 16, &metrics_dev_));
+    dev_.check(sl_clear(dev_.ctx(), metrics_dev_, 16));
+}
+
+bool Mlp::small_active(size_t batch) const {
+    return fused_ && loss_ == LOSS_SQUARED && sl_comm_nranks(dev_.ctx()) <= 1 &&
+           sl_mlp_small_fits(dev_.ctx(), (int)layers_.size(), dims_.data(), batch) != 0;
+}
+
+StepResult Mlp::step_small(const Buf& x, const Buf& y, size_t batch, double lr, bool want_metrics) {
+    dev_.flush_pending();
+    dev_.check(sl_mlp_small_step(dev_.ctx(), SL_F32, (int)layers_.size(), dims_.data(), seg_off_.data(), batch, x->dptr, y->dptr, params_->dptr,
+                                 bucket_->dptr, lr, metrics_dev_));
+    return read_metrics(want_metrics);
 }
 
 Mlp::~Mlp() {
@@ -61,7 +74,7 @@ StepResult Mlp::step_replay(const Buf& x, const Buf& y, const Buf& labels, size_
     }
     // a captured step must be allocation-free: the op-by-op tape only is on a Cached device (same buffers every iteration);
     // the fused softmax-cce step keeps its own persistent activations
-    if (!dev_.cached() && !(fused_ && loss_ == LOSS_SOFTMAX_CCE))
+    if (!dev_.cached() && !(fused_ && loss_ == LOSS_SOFTMAX_CCE) && !small_active(batch))
         throw Error(SL_ERR_INVALID_ARG, "Mlp::step_replay: needs a Cached device (or the fused step): a captured step may not allocate or free");
     StepResult r = step(x, y, labels, batch, grad_rows, lr, want_metrics);   // this call's step, eagerly (creates every buffer)
     dev_.check(sl_graph_begin(dev_.ctx()));
@@ -185,12 +198,12 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
     // ---- backward: the tape of nn.rs in reverse, with gemm_grad(lhs) + relu grad fused
     // Data-parallel schedule knobs (read per call, so a sweep can change them at run time; all bit-identical in their results):
     //   SLICED_DP_CHUNKS   the step's LAST weight-gradient gemm is produced in this many row blocks, each handed to the exchange as it
-    //                      completes: the one exchange with no later gemm to hide behind shrinks to its last block.  Default 4 with a
-    //                      communicator, 1 without.  SLICED_DP_CHUNKS_ALL=1 chunks every layer's weight gradient.
+    //                      completes: the one exchange with no later gemm to hide behind shrinks to its last block.  Default 1: with the
+    //                      launch-control gemm schedule one exchange per layer measured fastest at N=8 (profiles/r2c_dp_sweep_n8.txt:
+    //                      4.25 ms vs 4.38 with 4 blocks).  SLICED_DP_CHUNKS_ALL=1 chunks every layer's weight gradient.
     //   SLICED_DP_ORDER    0: per layer dW then dX (tape order); 1: the dX chain first, then the weight gradients from the input layer
     //                      up (the exchanges of the early ones hide behind the later gemms)
-    const bool dp = sl_comm_nranks(c) > 1;
-    const int dp_chunks = env_int("SLICED_DP_CHUNKS", dp ? 4 : 1);
+    const int dp_chunks = env_int("SLICED_DP_CHUNKS", 1);
     const bool chunk_all = env_int("SLICED_DP_CHUNKS_ALL", 0) != 0;
     const int order = env_int("SLICED_DP_ORDER", 0);
     layer_exchanges_.assign(L, 0);

@@ -66,7 +66,12 @@ class Mlp {
     void allreduce_grads();          // sl_allreduce_sum over the bucket (no-op for a world of one)
     void sgd(double lr);             // SGD::step on every Linear (nn.rs:235-237)
     void exchange_and_sgd(double lr);  // both, with the update of each layer issued as soon as its exchange has completed
+    // fused + squared loss + a shape sl_mlp_small_step takes (<= 4 layers of width <= 64, one rank): the WHOLE step, SGD included, is one
+    // launch of one thread-block cluster (csrc/mlp_small.cu) — examples/sine_net.rs at its shipped sizes
+    bool small_active(size_t batch) const;
+    StepResult step_small(const Buf& x, const Buf& y, size_t batch, double lr, bool want_metrics);
     StepResult step(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, double lr, bool want_metrics) {
+        if (small_active(batch) && grad_rows == batch) return step_small(x, y, batch, lr, want_metrics);
         StepResult r = (fused_ && loss_ == LOSS_SOFTMAX_CCE) ? forward_backward_fused(x, y, labels, batch, grad_rows, want_metrics)
                                                                 : forward_backward(x, y, labels, batch, grad_rows, want_metrics);
         exchange_and_sgd(lr);

@@ -307,3 +307,92 @@ def test_sine_net_1000_steps_against_fp64_yardstick_and_teacher_forced_parity():
                 assert np.max(np.abs(mlp.bias(l).read() - Bo[l])) <= 1e-5 * max(np.max(np.abs(Bo[l])), 1e-3), (k, l)
     del mlp, dx, dy
     dev.close()
+
+
+def _run_small(dims, x, y, W, B, lr, steps, fused, replay=False):
+    from sliced_b200.host import CUDA, Mlp
+    dev = CUDA(0, cached=True)
+    mlp = Mlp(dev, dims, 1)
+    mlp.set_fused(fused)
+    for l in range(len(dims) - 1):
+        mlp.weights(l).write(W[l]); mlp.bias(l).write(B[l])
+    batch = x.size // dims[0]
+    dx, dy = dev.buffer(x).no_grad(), dev.buffer(y).no_grad()
+    fn = mlp.step_replay if replay else mlp.step
+    l0 = dev.launches
+    hist = [fn(dx, dy, None, batch, lr)[0] for _ in range(steps)]
+    res = (hist, mlp.params().read(), mlp.grad_bucket().read(), dev.launches - l0)
+    del mlp, dx, dy
+    dev.close()
+    return res
+
+
+@pytest.mark.parametrize("dims,batch,taken", [([1, 64, 64, 1], 1000, True), ([3, 17, 5, 2], 37, True), ([8, 64, 1], 5000, True), ([5, 7], 3, True),
+                                              ([64, 48, 32, 48, 64], 2500, True), ([2, 33, 1], 1, True),
+                                              ([64, 64, 64, 64, 64], 100, False),    # four 64 x 64 layers do not fit in shared memory
+                                              ([1, 65, 1], 100, False)])             # wider than 64: the op-by-op tape runs instead
+def test_small_step_matches_tape_and_oracle(dims, batch, taken):
+    """sl_mlp_small_step (the whole squared-error step in one cluster launch, examples/sine_net.rs:135-163) against the op-by-op tape
+    and the oracle's replay: per-step loss, the parameter gradients of the last step and the parameters after 3 steps.  Ragged widths,
+    one sample, more samples than one pass holds, 1..4 layers."""
+    x, y, _, W, B = make_problem(dims, batch, 11, classes=False)
+    for b in B:
+        b += np.random.default_rng(5).uniform(-0.05, 0.05, b.size).astype(np.float32)
+    steps, lr = 3, 1e-3
+    Wo, Bo = [w.copy() for w in W], [b.copy() for b in B]
+    ref = [O.mlp_step(1, dims, x, y, None, Wo, Bo, lr)[0] for _ in range(steps)]
+    h0, p0, g0, n0 = _run_small(dims, x, y, W, B, lr, steps, fused=False)
+    h1, p1, g1, n1 = _run_small(dims, x, y, W, B, lr, steps, fused=True)
+    assert (n1 == steps) == taken, "one launch per step exactly for the shapes sl_mlp_small_fits takes"
+    for a, b, c in zip(h1, h0, ref):
+        assert abs(a - b) <= 5e-6 * abs(b) + 1e-7, (a, b)
+        assert abs(a - c) <= 5e-6 * abs(c) + 1e-7, (a, c)
+    assert np.max(np.abs(g1 - g0)) <= 2e-5 * np.max(np.abs(g0)), np.max(np.abs(g1 - g0))
+    assert np.max(np.abs(p1 - p0)) <= 1e-6 * np.max(np.abs(p0)), np.max(np.abs(p1 - p0))
+    off = 0
+    for l in range(len(dims) - 1):   # flat layout [W0 | b0 | W1 | ...], every segment padded to 64 floats
+        for ref_seg in (Wo[l], Bo[l]):
+            seg = p1[off:off + ref_seg.size]
+            assert np.max(np.abs(seg - ref_seg)) <= 1e-5 * max(np.max(np.abs(ref_seg)), 1e-3)
+            off += (ref_seg.size + 63) // 64 * 64
+
+
+def test_small_step_relu_mask_is_on_the_pre_activation():
+    """relu' is (z >= 0) on the layer INPUT (matrix.rs:181-188): a unit whose pre-activation is exactly 0 passes the gradient"""
+    dims, batch = [2, 4, 1], 8
+    x = np.zeros(batch * 2, np.float32)          # z1 = 0 * W + 0 = 0 everywhere -> mask 1, a1 = 0
+    y = np.ones(batch, np.float32)
+    W = [np.full(8, 0.5, np.float32), np.full(4, 0.25, np.float32)]
+    B = [np.zeros(4, np.float32), np.zeros(1, np.float32)]
+    h0, p0, g0, _ = _run_small(dims, x, y, W, B, 0.1, 1, fused=False)
+    h1, p1, g1, _ = _run_small(dims, x, y, W, B, 0.1, 1, fused=True)
+    assert h0 == h1
+    assert np.array_equal(g0, g1) and np.any(g1[64:68] != 0), "bias gradient of the hidden layer flows through z == 0"
+    assert np.array_equal(p0, p1)
+
+
+def test_small_step_sine_net_1000_steps_and_replay():
+    """examples/sine_net.rs, 1001 steps of the one-launch step: ends within the measured fp32 spread of the fp64 replay (the trajectory is
+    chaotic, see test_sine_net_1000_steps_against_fp64_yardstick_and_teacher_forced_parity) and teacher-forced single steps reproduce the
+    oracle's; CUDA-graph replay of the launch is bit-identical to launching it."""
+    from tests import sine_replay as SR
+    xs, ys, W, B = SR.problem()
+    hist, _, _, launches = _run_small(SR.DIMS, xs, ys, W, B, 1e-4, 1001, fused=True)
+    assert launches == 1001
+    gpu = np.array(hist)
+    l64 = SR.replay(np.float64, 1001, W, xs, ys)
+    assert np.all(np.abs(gpu[:10] - l64[:10]) <= 1e-5 * l64[:10])
+    print(f"sine_net (one-launch step) loss after 1001 steps: gpu {gpu[1000] / 1000:.6f} fp64 {l64[1000] / 1000:.6f}")
+    assert abs(gpu[1000] - l64[1000]) <= 0.10 * l64[1000]
+    hist_r, p_r, _, _ = _run_small(SR.DIMS, xs, ys, W, B, 1e-4, 50, fused=True, replay=True)
+    hist_e, p_e, _, _ = _run_small(SR.DIMS, xs, ys, W, B, 1e-4, 50, fused=True)
+    assert hist_r == hist_e and np.array_equal(p_r, p_e)
+    Wo, Bo = [w.copy() for w in W], [b.copy() for b in B]
+    for k in range(301):
+        if k % 100 == 0:
+            l_gpu, p, _, _ = _run_small(SR.DIMS, xs, ys, Wo, Bo, 1e-4, 1, fused=True)
+        l_ref = O.mlp_step(1, SR.DIMS, xs, ys, None, Wo, Bo, 1e-4)[0]
+        if k % 100 == 0:
+            assert abs(l_gpu[0] - l_ref) <= 2e-6 * abs(l_ref), (k, l_gpu, l_ref)
+            assert np.max(np.abs(p[64:64 + 64] - Bo[0])) <= 1e-5 * max(np.max(np.abs(Bo[0])), 1e-3)
+            assert np.max(np.abs(p[128:128 + 4096] - Wo[1])) <= 1e-5 * np.max(np.abs(Wo[1]))

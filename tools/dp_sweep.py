@@ -23,22 +23,18 @@ import torch.distributed as dist
 
 import bench as BN
 
-KNOBS = ("SLICED_DP_NOCOMM", "SLICED_DP_CHUNKS", "SLICED_DP_CHUNKS_ALL", "SLICED_DP_ORDER", "SLICED_DP_LAYER_SGD", "SLICED_GEMM_RESERVE_SMS", "SLICED_GEMM_MAX_SPLITS")
+KNOBS = ("SLICED_DP_NOCOMM", "SLICED_DP_CHUNKS", "SLICED_DP_CHUNKS_ALL", "SLICED_DP_ORDER", "SLICED_DP_LAYER_SGD", "SLICED_GEMM_RESERVE_SMS", "SLICED_GEMM_MAX_SPLITS",
+         "SLICED_GEMM_SCHED")
 CONFIGS = [
-    ("r1 schedule: 1 exchange/layer, flat SGD", dict(SLICED_DP_CHUNKS="1", SLICED_DP_LAYER_SGD="0")),
-    ("per-layer SGD", dict(SLICED_DP_CHUNKS="1", SLICED_DP_LAYER_SGD="1")),
-    ("chunks 2", dict(SLICED_DP_CHUNKS="2")),
-    ("chunks 4 (default)", dict(SLICED_DP_CHUNKS="4")),
-    ("chunks 8", dict(SLICED_DP_CHUNKS="8")),
-    ("chunks 4, flat SGD", dict(SLICED_DP_CHUNKS="4", SLICED_DP_LAYER_SGD="0")),
-    ("chunks 4, every layer", dict(SLICED_DP_CHUNKS="4", SLICED_DP_CHUNKS_ALL="1")),
-    ("chunks 4, dX-first order", dict(SLICED_DP_CHUNKS="4", SLICED_DP_ORDER="1")),
-    ("chunks 1, dX-first order", dict(SLICED_DP_CHUNKS="1", SLICED_DP_ORDER="1")),
-    ("chunks 4, reserve 4 SMs", dict(SLICED_DP_CHUNKS="4", SLICED_GEMM_RESERVE_SMS="4")),
-    ("chunks 4, reserve 8 SMs", dict(SLICED_DP_CHUNKS="4", SLICED_GEMM_RESERVE_SMS="8")),
-    ("chunks 1, reserve 8 SMs", dict(SLICED_DP_CHUNKS="1", SLICED_GEMM_RESERVE_SMS="8")),
-    ("chunks 4, no split-K", dict(SLICED_DP_CHUNKS="4", SLICED_GEMM_MAX_SPLITS="1")),
-    ("chunks 1, split-K up to 4 always", dict(SLICED_DP_CHUNKS="1", SLICED_GEMM_MAX_SPLITS="4")),
+    ("static schedule, chunks 4 (r2 default)", dict(SLICED_GEMM_SCHED="0", SLICED_DP_CHUNKS="4")),
+    ("static schedule, chunks 1", dict(SLICED_GEMM_SCHED="0", SLICED_DP_CHUNKS="1")),
+    ("launch control, chunks 1", dict(SLICED_GEMM_SCHED="1", SLICED_DP_CHUNKS="1")),
+    ("launch control, chunks 2", dict(SLICED_GEMM_SCHED="1", SLICED_DP_CHUNKS="2")),
+    ("launch control, chunks 4", dict(SLICED_GEMM_SCHED="1", SLICED_DP_CHUNKS="4")),
+    ("launch control, chunks 4, every layer", dict(SLICED_GEMM_SCHED="1", SLICED_DP_CHUNKS="4", SLICED_DP_CHUNKS_ALL="1")),
+    ("launch control, chunks 1, dX-first order", dict(SLICED_GEMM_SCHED="1", SLICED_DP_CHUNKS="1", SLICED_DP_ORDER="1")),
+    ("launch control, chunks 1, flat SGD", dict(SLICED_GEMM_SCHED="1", SLICED_DP_CHUNKS="1", SLICED_DP_LAYER_SGD="0")),
+    ("launch control, chunks 1, no split-K", dict(SLICED_GEMM_SCHED="1", SLICED_DP_CHUNKS="1", SLICED_GEMM_MAX_SPLITS="1")),
 ]
 
 
@@ -101,6 +97,7 @@ def main():
                 step()
             res[name].append(timed(step, args.steps)[0])
     set_knobs({})
+    nccl_env = {k: v for k, v in os.environ.items() if k.startswith("NCCL_")}
     # the step without its exchange (wrong numbers, right cost): the per-GPU compute share, and how far apart the ranks run
     os.environ["SLICED_DP_NOCOMM"] = "1"
     for _ in range(3):
@@ -116,7 +113,8 @@ def main():
         for _ in range(3):
             f()
     t_w, t_all = timed(ar_w, 20), timed(ar_all, 20)
-    lines = [f"# data-parallel schedule sweep, N={world}, per-GPU batch {batch} ({args.scaling}), {args.steps} steps x {args.passes} passes, ms/step = max over ranks",
+    lines = [f"# NCCL environment: {nccl_env}",
+             f"# data-parallel schedule sweep, N={world}, per-GPU batch {batch} ({args.scaling}), {args.steps} steps x {args.passes} passes, ms/step = max over ranks",
              f"# bare NCCL all-reduce (alone on the GPU): one weight gradient {nW * 4 / 1e6:.0f} MB {t_w[0]:.3f} ms; whole bucket {mlp.n_params * 4 / 1e6:.0f} MB {t_all[0]:.3f} ms",
              f"# step without any exchange (per-GPU compute only): slowest rank {t_nc[0]:.3f} ms, fastest rank {t_nc[1]:.3f} ms",
              f"# {'configuration':40s} " + " ".join(f"pass{p}" for p in range(args.passes)) + "    best"]

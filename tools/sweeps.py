@@ -244,9 +244,10 @@ def run_sine_net(device_index=0, iters=300):
     rng = np.random.default_rng(0)
     W0 = [rng.uniform(-0.5, 0.5, dims[i] * dims[i + 1]).astype(np.float32) for i in range(3)]
     out = {}
-    for mode in ("eager", "graph"):
+    for mode in ("eager", "graph", "one_launch"):   # one_launch: sl_mlp_small_step (the whole step in one cluster launch)
         dev = CUDA(device_index, cached=True)
         mlp = Mlp(dev, dims, 1)
+        mlp.set_fused(mode == "one_launch")
         for l in range(3):
             mlp.weights(l).write(W0[l])
         dx, dy = dev.buffer(xs).no_grad(), dev.buffer(ys).no_grad()
