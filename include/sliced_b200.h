@@ -304,6 +304,16 @@ int sl_linear_fwd(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const vo
  * == sl_gemm_grad(lhs_grad only) followed by sl_unary_grad(SL_UN_RELU) into a zeroed gradient (ops.rs:260-275, matrix.rs:183-188). f32. */
 int sl_linear_bwd_input_relu(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* rhs, const void* out_grad, const void* z_prev,
                              void* x_grad, int mode);
+/* The same two fused products with the relu mask carried as ONE BIT per element instead of the pre-activation matrix
+ * (mask_bits: uint32 [m x ceil(cols / 32)], bit c % 32 of word c / 32 of row r = (z[r][c] >= 0), cols = n for the forward, k for the
+ * gradient): the forward stores relu(z) only, the gradient reads 1/32 of the bytes.  Results are bit-identical to sl_linear_fwd's
+ * act_out and to sl_linear_bwd_input_relu (the mask of src/matrix.rs:181-188 is exactly this bit).  On the 2-CTA tensor-core path
+ * (cols % 32 == 0) and in the skinny head kernel the bits are produced / consumed in the gemm epilogue; other shapes take an extra
+ * element-wise pass.  f32. */
+int sl_linear_fwd_bits(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, const void* bias, void* act_out,
+                       uint32_t* mask_bits, int mode);
+int sl_linear_bwd_input_relu_bits(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* rhs, const void* out_grad,
+                                  const uint32_t* mask_bits, void* x_grad, int mode);
 
 /* ---------------------------------------------------------------- R: reductions */
 

@@ -120,6 +120,8 @@ def _declare(lib):
         "sl_gemm_scope_end": ([_vp], _i),
         "sl_linear_fwd": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _i], _i),
         "sl_linear_bwd_input_relu": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _i], _i),
+        "sl_linear_fwd_bits": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _i], _i),
+        "sl_linear_bwd_input_relu_bits": ([_vp, _i, _sz, _sz, _sz, _vp, _vp, _vp, _vp, _i], _i),
         "sl_sum": ([_vp, _i, _vp, _sz, _vp], _i),
         "sl_mean": ([_vp, _i, _vp, _sz, _vp], _i),
         "sl_max": ([_vp, _i, _vp, _sz, _vp], _i),

@@ -216,9 +216,11 @@ __global__ void __launch_bounds__(256) smallout_tn_kernel(size_t m, size_t n, si
 // Thread owns 4 consecutive output columns: their B rows (4 x KP) live in registers for the whole kernel.  A CTA covers
 // 1024 columns and a slab of rows whose A values ([rows x KP], padded to KP + 2) are staged in shared memory and read as
 // broadcasts.  Optional fused epilogue: out *= (mask_src >= 0) (the relu gradient that follows this gemm in the MLP).
-template <int KP, bool ACC, bool MASK>
+// MASK 1: the mask source is the pre-activation matrix (4 bytes per element); MASK 2: one bit per element ([m x n/32] words, n % 32 == 0).
+template <int KP, bool ACC, int MASK>
 __global__ void __launch_bounds__(256) skinny_nt_kernel(size_t m, size_t n, size_t k, size_t rows_per_block, const float* __restrict__ A,
-                                                        const float* __restrict__ B, float* C, const float* __restrict__ mask_src) {
+                                                        const float* __restrict__ B, float* C, const float* __restrict__ mask_src,
+                                                        const uint32_t* __restrict__ mask_bits) {
     constexpr int LDA = KP + 2;
     extern __shared__ __align__(16) float As[];
     const size_t r0 = (size_t)blockIdx.y * rows_per_block;
@@ -238,7 +240,9 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(size_t m, size_t n, size
 #pragma unroll
         for (int q = 0; q < KP; ++q) b[e][q] = (size_t)q < k ? __ldg(B + (j0 + e) * k + q) : 0.f;
     float* cp = C + r0 * n + j0;
-    const float* mp = MASK ? mask_src + r0 * n + j0 : nullptr;
+    const float* mp = MASK == 1 ? mask_src + r0 * n + j0 : nullptr;
+    const uint32_t* bp = MASK == 2 ? mask_bits + r0 * (n >> 5) + (j0 >> 5) : nullptr;
+    const int bshift = (int)(j0 & 31);
 #pragma unroll 4
     for (size_t r = 0; r < rows; ++r) {
         const float2* ap = reinterpret_cast<const float2*>(As + r * LDA);
@@ -253,7 +257,11 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(size_t m, size_t n, size
             const float4 c = *reinterpret_cast<const float4*>(cp + r * n);
             o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
         }
-        if (MASK) {
+        if (MASK == 2) {
+            const uint32_t w = __ldg(bp + r * (n >> 5)) >> bshift;
+            o.x = (w & 1u ? 1.f : 0.f) * o.x; o.y = (w & 2u ? 1.f : 0.f) * o.y; o.z = (w & 4u ? 1.f : 0.f) * o.z; o.w = (w & 8u ? 1.f : 0.f) * o.w;
+        }
+        if (MASK == 1) {
             const Pack<float> mk = ld_stream(mp + r * n);
             o.x = (mk.v[0] >= 0.f ? 1.f : 0.f) * o.x; o.y = (mk.v[1] >= 0.f ? 1.f : 0.f) * o.y;
             o.z = (mk.v[2] >= 0.f ? 1.f : 0.f) * o.z; o.w = (mk.v[3] >= 0.f ? 1.f : 0.f) * o.w;
@@ -280,8 +288,9 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(size_t m, size_t n, size
 // returns SL_OK when a skinny kernel handled the call, 1 when the shape is not skinny (caller falls through).
 // mask_src (nt shape only): fused `C *= (mask_src >= 0)`; *mask_done tells the caller whether it was applied.
 int sl_gemm_skinny_f32(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const float* a, const float* b, float* c,
-                       int accumulate, const float* mask_src, int* mask_done) {
+                       int accumulate, const float* mask_src, int* mask_done, const uint32_t* mask_bits) {
     if (mask_done) *mask_done = 0;
+    if (mask_bits && (n % 32 != 0 || mask_src)) mask_bits = nullptr;   // (the caller applies the bits itself when *mask_done stays 0)
     const bool al = sl_aligned16(a) && sl_aligned16(b) && sl_aligned16(c);
     if (!trans_a && !trans_b && n >= 1 && n <= 16 && k >= 256 && m >= 64 && k % 4 == 0 && al) {
         const int np = (int)((n + 1) & ~size_t(1));
@@ -368,14 +377,16 @@ int sl_gemm_skinny_f32(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n
 #define SK_NT(ACCV, MASKV)                                                                                                              \
     SK_DISPATCH(kp, {                                                                                                                   \
         SL_CUDA(ctx, cudaFuncSetAttribute(skinny_nt_kernel<NP, ACCV, MASKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
-        SL_LAUNCH(ctx, (skinny_nt_kernel<NP, ACCV, MASKV>), grid, 256, smem, m, n, k, rpb, a, b, c, mask_src);                          \
+        SL_LAUNCH(ctx, (skinny_nt_kernel<NP, ACCV, MASKV>), grid, 256, smem, m, n, k, rpb, a, b, c, mask_src, mask_bits);               \
     })
-            if (accumulate && mask_src) SK_NT(true, true)
-            else if (accumulate) SK_NT(true, false)
-            else if (mask_src) SK_NT(false, true)
-            else SK_NT(false, false)
+            if (accumulate && mask_src) SK_NT(true, 1)
+            else if (accumulate && mask_bits) SK_NT(true, 2)
+            else if (accumulate) SK_NT(true, 0)
+            else if (mask_src) SK_NT(false, 1)
+            else if (mask_bits) SK_NT(false, 2)
+            else SK_NT(false, 0)
 #undef SK_NT
-            if (mask_src && mask_done) *mask_done = 1;
+            if ((mask_src || mask_bits) && mask_done) *mask_done = 1;
             return SL_OK;
         }
     }

@@ -30,7 +30,7 @@
 int sl_gemm_simt(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t m, size_t n, size_t k, const void* a, const void* b, void* c,
                  int accumulate);
 int sl_gemm_skinny_f32(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n, size_t k, const float* a, const float* b, float* c,
-                       int accumulate, const float* mask_src, int* mask_done);
+                       int accumulate, const float* mask_src, int* mask_done, const uint32_t* mask_bits = nullptr);
 
 namespace {
 
@@ -219,6 +219,11 @@ struct GemmParams {
     int debug;              // bit 0: skip the final store (timing experiments only, SLICED_GEMM_DEBUG)
     unsigned long long hint_a, hint_b;   // L2 eviction-priority policy of the A / B operand loads (0 = none)
     int dynamic;            // 2-CTA kernel: 1 = one cluster per work unit, units handed out by cluster launch control (work stealing)
+    // relu mask carried as one bit per element ([M x bits_words] uint32, bit c%32 of word c/32; N % 32 == 0, 2-CTA kernel only):
+    uint32_t* bits_out;          //   written: (v >= 0) of the value after bias, before the in-place relu
+    const uint32_t* bits_in;     //   read: v *= bit (the relu gradient) — replaces mask_src (4 bytes per element) by 1/32 of the traffic
+    int bits_words;
+    unsigned long long* stats;   // SLICED_GEMM_STATS (diagnosis): per leader CTA [total, wait full, wait tmem_empty, store phase, units] clocks
 };
 
 // shared epilogue arithmetic of both MMA kernels: 4 consecutive columns of one output row
@@ -504,7 +509,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
     return r;
 }
+// Arrival on a barrier of the pair's leader.  Default semantics (release at CTA scope): what the arrival has to order is this warp's
+// tcgen05.ld of the accumulator chunk (tcgen05.fence::before_thread_sync does that) — a cluster-scope release additionally made the
+// warp wait for every global store of the previous tile's store phase to be acknowledged (ncu: 13 % of all samples in ERRBAR).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {   // SLICED_GEMM_DEBUG bit 1: the old form, for A/B timing
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose mbarrier may live in the peer CTA of the pair (the leader's full barrier)
@@ -836,18 +847,30 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             uint32_t phase = 0;
             uint32_t g = 0;
             uint32_t it = 0;
+            long long st_t0 = p.stats ? clock64() : 0, st_full = 0, st_empty = 0, st_units = 0;
             for (int unit = cluster_id; unit >= 0; unit = next_unit(unit, it, false)) {
                 const int kb0 = (unit % splits) * kbs, kb1 = min(num_kb, kb0 + kbs);
                 const int num_chunks = chunk_count(kb1 - kb0);
+                ++st_units;
                 for (int ch = 0; ch < num_chunks; ++ch, ++g) {
                     const uint32_t buf = g & 1;
-                    mbar_wait(tmem_empty_bar(buf), ((g >> 1) & 1) ^ 1);
+                    if (p.stats) {
+                        const long long t = clock64();
+                        mbar_wait(tmem_empty_bar(buf), ((g >> 1) & 1) ^ 1);
+                        st_empty += clock64() - t;
+                    } else
+                        mbar_wait(tmem_empty_bar(buf), ((g >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + buf * Cfg::TILE_N;
                     const int kb_begin = kb0 + chunk_begin(ch);
                     const int kb_end = min(kb1, kb0 + chunk_begin(ch + 1));
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
-                        mbar_wait(full_bar(stage), phase);
+                        if (p.stats) {
+                            const long long t = clock64();
+                            mbar_wait(full_bar(stage), phase);
+                            st_full += clock64() - t;
+                        } else
+                            mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
                         const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                         const uint32_t sb = sa + Cfg::PLANES * Cfg::A_BYTES;
@@ -877,6 +900,10 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                     }
                     umma_commit_2sm(tmem_full_bar(buf), 0x3);     // chunk complete -> both CTAs' epilogues
                 }
+            }
+            if (p.stats) {
+                unsigned long long* o = p.stats + (size_t)(blockIdx.x >> 1) * 8;
+                o[0] = clock64() - st_t0; o[1] = st_full; o[2] = st_empty; o[4] = st_units;
             }
         }
         __syncwarp();
@@ -928,10 +955,14 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_shared(tmem_empty_bar(buf), 0));  // the leader's barrier
+                if (lane == 0) {   // the leader's barrier
+                    if (p.debug & 2) mbar_arrive_cluster_release(mapa_shared(tmem_empty_bar(buf), 0));
+                    else mbar_arrive_cluster(mapa_shared(tmem_empty_bar(buf), 0));
+                }
             }
             const int row = m_blk * Cfg::TILE_M + (int)rank * 128 + quad * 32 + lane;
             if (p.debug & 1) continue;
+            const long long st_s0 = p.stats ? clock64() : 0;
             if (p.c_vec_ok) {
                 // coalesced path: 32 x 32 blocks through the warp's shared-memory tile
                 float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + ew * 1024;
@@ -940,6 +971,15 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                 const float rs = (p.row_scale && row < p.M) ? __ldg(p.row_scale + row) : 1.f;
                 const size_t tile_off = (size_t)row_base * p.N;
                 float* cbase = p.C + (size_t)split * p.M * p.N + tile_off;
+                // relu-gradient mask bits of this row's CPW columns: requested together, one L2 round trip per tile
+                uint32_t wbits[CPW / 32];
+                if (p.bits_in) {
+#pragma unroll
+                    for (int c = 0; c < CPW / 32; ++c) {
+                        const int n0 = n_blk * Cfg::TILE_N + col0 + c * 32;
+                        wbits[c] = (row < p.M && n0 < p.N) ? __ldg(p.bits_in + (size_t)row * p.bits_words + (n0 >> 5)) : 0u;
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < CPW / 32; ++c) {
                     const int n0 = n_blk * Cfg::TILE_N + col0 + c * 32;
@@ -965,6 +1005,16 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                             }
                     }
                     if (p.mask_src) epi_gather<true>(stage, lane, v, p.mask_src + tile_off + n0, (size_t)p.N, rows_valid, cols_valid);
+                    if (p.bits_in) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = ((wbits[c] >> j) & 1u ? 1.f : 0.f) * v[j];
+                    }
+                    if (p.bits_out) {
+                        uint32_t w = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) w |= (v[j] >= 0.f ? 1u : 0u) << j;
+                        if (row < p.M) p.bits_out[(size_t)row * p.bits_words + (n0 >> 5)] = w;
+                    }
                     if (p.relu) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = (v[j] >= 0.f ? 1.f : 0.f) * v[j];
@@ -993,6 +1043,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                     }
                 }
             }
+            if (p.stats && leader && warp == 2 && lane == 0) p.stats[(size_t)(blockIdx.x >> 1) * 8 + 3] += clock64() - st_s0;
         }
     }
 
@@ -1367,7 +1418,32 @@ static int launch_cfg_2cta(sl_ctx* ctx, const GemmParams& p, const void* a_hi, c
         rec.flops = 2.0 * p.M * (double)p.N * p.K;
         cudaEventRecord(rec.a, ctx->stream);
     }
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    static unsigned long long* stats_dev = nullptr;
+    const bool want_stats = env_int("SLICED_GEMM_STATS", 0) != 0;
+    GemmParams ps = p;
+    if (want_stats) {   // diagnosis only: synchronous, prints where the MMA issuer's clocks went
+        if (!stats_dev) cudaMalloc(&stats_dev, 8 * sizeof(unsigned long long) * 65536);
+        cudaMemsetAsync(stats_dev, 0, 8 * sizeof(unsigned long long) * (size_t)(grid / 2 < 65536 ? grid / 2 : 65536), ctx->stream);
+        if (grid / 2 <= 65536) ps.stats = stats_dev;
+    }
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, ps);
+    if (ps.stats) {
+        cudaStreamSynchronize(ctx->stream);
+        std::vector<unsigned long long> h((size_t)(grid / 2) * 8);
+        cudaMemcpy(h.data(), stats_dev, h.size() * 8, cudaMemcpyDeviceToHost);
+        double tot = 0, full = 0, empty = 0, store = 0, units = 0, active = 0, tmax = 0;
+        for (int c = 0; c < grid / 2; ++c) {
+            if (!h[(size_t)c * 8 + 4]) continue;   // cluster whose unit was taken over before it launched
+            active += 1; tot += h[(size_t)c * 8]; full += h[(size_t)c * 8 + 1]; empty += h[(size_t)c * 8 + 2]; store += h[(size_t)c * 8 + 3];
+            units += h[(size_t)c * 8 + 4];
+            if (h[(size_t)c * 8] > tmax) tmax = (double)h[(size_t)c * 8];
+        }
+        printf("gemm stats M %d N %d K %d splits %d A_MN %d B_MN %d mask %d relu %d: clusters %.0f units %.0f | MMA issuer clocks avg %.0f max %.0f | wait operands %.1f%% | "
+               "wait tmem-empty %.1f%% | store phase per unit %.0f clocks (budget %d k-blocks)\n",
+               p.M, p.N, p.K, p.splits, (int)A_MN, (int)B_MN, p.mask_src != nullptr, p.relu, active, units, tot / active, tmax, 100. * full / tot, 100. * empty / tot,
+               store / units, 2 * (p.kc_first > p.kc_blocks ? p.kc_first : p.kc_blocks));
+        fflush(stdout);
+    }
     ctx->launches++;
     if (ctx->profiling) {
         cudaEventRecord(rec.b, ctx->stream);
@@ -1396,14 +1472,21 @@ static int sl_gemm_pick_cfg(sl_ctx* ctx, size_t M, size_t N) {
 }
 
 // folds split-K partials in split order and applies the epilogue (see sl_gemm_tc_planes)
+// (mask bits: n % 32 == 0, so the 32 consecutive elements of a warp are the 32 bits of one word)
 __global__ void __launch_bounds__(256) splitk_fold_kernel(size_t total, size_t n, int splits, const float* __restrict__ partial, float* C, int accumulate,
-                                                          const float* __restrict__ bias, int relu, float* C2, const float* __restrict__ mask_src) {
+                                                          const float* __restrict__ bias, int relu, float* C2, const float* __restrict__ mask_src,
+                                                          const uint32_t* __restrict__ bits_in, uint32_t* bits_out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         float v = partial[i];
         for (int s = 1; s < splits; ++s) v += partial[(size_t)s * total + i];
         if (accumulate) v += C[i];
         if (bias) v += __ldg(bias + i % n);
         if (mask_src) v = (__ldg(mask_src + i) >= 0.f ? 1.f : 0.f) * v;
+        if (bits_in) v = ((__ldg(bits_in + (i >> 5)) >> (i & 31)) & 1u ? 1.f : 0.f) * v;
+        if (bits_out) {
+            const uint32_t w = __ballot_sync(0xffffffffu, v >= 0.f);
+            if ((threadIdx.x & 31) == 0) bits_out[i >> 5] = w;
+        }
         if (relu) v = (v >= 0.f ? 1.f : 0.f) * v;
         C[i] = v;
         if (C2) C2[i] = (v >= 0.f ? 1.f : 0.f) * v;
@@ -1416,9 +1499,11 @@ __global__ void __launch_bounds__(256) splitk_fold_kernel(size_t total, size_t n
 // hold the inverse operand scales applied by the epilogue.
 int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const void* a_lo, size_t lda, const void* b_hi, const void* b_lo,
                       size_t ldb, float* C, const float* bias, int accumulate, int relu, float* c2, const float* mask_src, int a_mn, int b_mn,
-                      int kind = 0, const float* row_scale = nullptr, const float* col_scale = nullptr) {
+                      int kind = 0, const float* row_scale = nullptr, const float* col_scale = nullptr, const uint32_t* bits_in = nullptr,
+                      uint32_t* bits_out = nullptr) {
     GemmParams p;
     p.M = M; p.N = N; p.K = K; p.C = C; p.bias = bias; p.accumulate = accumulate; p.relu = relu; p.C2 = c2; p.mask_src = mask_src;
+    p.bits_in = bits_in; p.bits_out = bits_out; p.bits_words = (N + 31) / 32; p.stats = nullptr;
     p.row_scale = row_scale; p.col_scale = col_scale;
     p.debug = env_int("SLICED_GEMM_DEBUG", 0);
     p.dynamic = env_int("SLICED_GEMM_SCHED", 1) != 0;   // 0: static persistent schedule | 1 (default): cluster launch control
@@ -1446,6 +1531,8 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
     //                                       | 4: 2-CTA pairs (cta_group::2), 256x256x32 per pair
     const int cfg = sl_gemm_pick_cfg(ctx, M, N);
     if (cfg != 4 && (a_mn || b_mn || kind)) return sl_set_error(ctx, SL_ERR_INVALID_ARG, "MN-major / fp16 planes need the 2-CTA kernel");
+    if ((bits_in || bits_out) && (cfg != 4 || !p.c_vec_ok || N % 32 != 0))
+        return sl_set_error(ctx, SL_ERR_INVALID_ARG, "mask bits need the 2-CTA kernel, N % 32 == 0 and aligned pointers");
     p.splits = 1;
     // Tile raster.  Measured on the MLP shapes (tools/raster_sweep.py): narrow groups win — with 2 blocks of the LONG dimension per
     // group the tiles running concurrently span the whole short dimension, so the smaller operand (the weights: 134 MB of hi/lo
@@ -1498,7 +1585,7 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
             if (rc != SL_OK) return rc;
             q.splits = best;
             q.C = (float*)ws;
-            q.bias = nullptr; q.accumulate = 0; q.relu = 0; q.C2 = nullptr; q.mask_src = nullptr;
+            q.bias = nullptr; q.accumulate = 0; q.relu = 0; q.C2 = nullptr; q.mask_src = nullptr; q.bits_in = nullptr; q.bits_out = nullptr;
             q.c_vec_ok = (N % 4 == 0);
         }
         int rc;
@@ -1515,7 +1602,7 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
         const size_t cap = (size_t)ctx->num_sms * 8;
         size_t blocks = (total + 255) / 256;
         SL_LAUNCH(ctx, splitk_fold_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, total, (size_t)N, best, (const float*)q.C, final_c, p.accumulate,
-                  p.bias, p.relu, p.C2, p.mask_src);
+                  p.bias, p.relu, p.C2, p.mask_src, p.bits_in, p.bits_out);
         return SL_OK;
     }
     const float *fa_hi = (const float*)a_hi, *fa_lo = (const float*)a_lo, *fb_hi = (const float*)b_hi, *fb_lo = (const float*)b_lo;
@@ -1588,8 +1675,34 @@ struct Epi {
     int relu = 0;
     float* c2 = nullptr;
     const float* mask_src = nullptr;
-    bool any() const { return bias || relu || c2 || mask_src; }
+    // the relu mask as one bit per element (see GemmParams): bits_out is taken before the in-place relu, bits_in multiplies like mask_src.
+    // Only the 2-CTA tensor-core path (and the skinny nt kernel for bits_in) fuses them: sl_linear_*_bits pick the path.
+    const uint32_t* bits_in = nullptr;
+    uint32_t* bits_out = nullptr;
+    bool any() const { return bias || relu || c2 || mask_src || bits_in || bits_out; }
 };
+
+// one thread per mask word: bits of z (row-major [rows x cols]) -> word, then relu in place.  Generic fallback of sl_linear_fwd_bits.
+__global__ void __launch_bounds__(256) bits_relu_kernel(size_t rows, size_t cols, size_t nw, float* z, uint32_t* bits) {
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < rows * nw; w += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = w / nw, c0 = (w % nw) * 32;
+        uint32_t m = 0;
+        for (int j = 0; j < 32 && c0 + j < cols; ++j) {
+            const float v = z[r * cols + c0 + j];
+            const bool pos = v >= 0.f;
+            m |= (pos ? 1u : 0u) << j;
+            z[r * cols + c0 + j] = (pos ? 1.f : 0.f) * v;
+        }
+        bits[w] = m;
+    }
+}
+// x[i] *= bit(i): generic fallback of sl_linear_bwd_input_relu_bits
+__global__ void __launch_bounds__(256) bits_apply_kernel(size_t rows, size_t cols, size_t nw, float* x, const uint32_t* __restrict__ bits) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * cols; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / cols, c = i % cols;
+        x[i] = ((__ldg(bits + r * nw + (c >> 5)) >> (c & 31)) & 1u ? 1.f : 0.f) * x[i];
+    }
+}
 
 // the same epilogue as a separate pass, for shapes that do not run on the tensor-core kernel (tiny / skinny)
 __global__ void __launch_bounds__(256) epilogue_pass_kernel(size_t total, size_t n, float* C, const float* __restrict__ bias, int relu, float* C2,
@@ -1727,7 +1840,7 @@ static int gemm_f16x3(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n,
         return SL_OK;
     }
     rc = sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, a_kc ? k : m, b_hi, b_lo, b_kc ? k : n, c, epi.bias, accumulate, epi.relu, epi.c2,
-                           epi.mask_src, a_kc ? 0 : 1, b_kc ? 0 : 1, 1, a_inv_use, b_inv_use);
+                           epi.mask_src, a_kc ? 0 : 1, b_kc ? 0 : 1, 1, a_inv_use, b_inv_use, epi.bits_in, epi.bits_out);
     if (rc == SL_OK && exchange_chunks) rc = sl_allreduce_sum_async(ctx, SL_F32, c, m * n);
     return rc;
 }
@@ -1757,9 +1870,12 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
         int rc = 1;
         int mask_done = 0;
         if (dtype == SL_F32 && mode != SL_GEMM_SIMT)  // HBM-bound skinny shapes (n <= 16 or k <= 16) have their own kernels
-            rc = sl_gemm_skinny_f32(ctx, trans_a, trans_b, m, n, k, (const float*)a, (const float*)b, (float*)c, accumulate, epi.mask_src, &mask_done);
+            rc = sl_gemm_skinny_f32(ctx, trans_a, trans_b, m, n, k, (const float*)a, (const float*)b, (float*)c, accumulate, epi.mask_src, &mask_done,
+                                    epi.bits_in);
         if (rc > 0) rc = sl_gemm_simt(ctx, dtype, trans_a, trans_b, m, n, k, a, b, c, accumulate);
         if (rc != SL_OK || !epi.any()) return rc;
+        if (epi.bits_out || (epi.bits_in && !mask_done))
+            return sl_set_error(ctx, SL_ERR_INVALID_ARG, "mask bits reached a kernel that cannot fuse them (internal: sl_linear_*_bits pick the path)");
         if (mask_done && !bias && !relu && !epi.c2) return SL_OK;   // the skinny kernel already applied the only epilogue term
         const size_t total = m * n;
         const size_t cap = (size_t)ctx->num_sms * 8;
@@ -1837,7 +1953,14 @@ static int gemm_ex_impl(sl_ctx* ctx, int dtype, int trans_a, int trans_b, size_t
         b_hi = h; b_lo = l; ldb = b_ld;
     }
     return sl_gemm_tc_planes(ctx, (int)m, (int)n, (int)k, a_hi, a_lo, lda, b_hi, b_lo, ldb, (float*)c, bias, accumulate, relu, epi.c2, epi.mask_src,
-                             a_mn ? 1 : 0, b_mn ? 1 : 0);
+                             a_mn ? 1 : 0, b_mn ? 1 : 0, 0, nullptr, nullptr, epi.bits_in, epi.bits_out);
+}
+
+// does gemm_ex_impl route this f32 product to the 2-CTA tensor-core kernel with a vectorised epilogue (the only sink that fuses mask bits)?
+static bool bits_fused_path(sl_ctx* ctx, int mode, size_t m, size_t n, size_t k, const void* c, const void* bias, const void* bits) {
+    if (mode < 0) mode = ctx->gemm_mode;
+    return mode != SL_GEMM_SIMT && tc_eligible(m, n, k) && sl_gemm_pick_cfg(ctx, m, n) == 4 && n % 32 == 0 && sl_aligned16(c) &&
+           (!bias || sl_aligned16(bias)) && bits && (reinterpret_cast<uintptr_t>(bits) & 3u) == 0;
 }
 
 extern "C" {
@@ -1879,6 +2002,63 @@ int sl_linear_bwd_input_relu(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t 
     e.mask_src = (const float*)z_prev;
     // gemmT(m, k, n, out_grad, rhs, x_grad) (gemm/grad/cpu_stack.rs:36) with the relu gradient (src/matrix.rs:186) in the epilogue
     return gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, x_grad, 0, mode, e);
+}
+
+int sl_linear_fwd_bits(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* rhs, const void* bias, void* act_out,
+                       uint32_t* mask_bits, int mode) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    SL_REQUIRE(ctx, dtype == SL_F32, "sl_linear_fwd_bits is f32 only");
+    SL_REQUIRE(ctx, act_out != nullptr && mask_bits != nullptr, "NULL output");
+    if (m == 0 || n == 0) return SL_OK;
+    sl_note_writes(ctx, act_out, mask_bits);
+    Epi e;
+    e.bias = (const float*)bias;
+    if (k > 0 && bits_fused_path(ctx, mode, m, n, k, act_out, bias, mask_bits)) {
+        e.relu = 1;
+        e.bits_out = mask_bits;
+        return gemm_ex_impl(ctx, dtype, 0, 0, m, n, k, lhs, rhs, act_out, 0, mode, e);
+    }
+    // any other shape: z = lhs * rhs + bias into act_out, then one pass takes the bits and applies the relu in place
+    int rc = gemm_ex_impl(ctx, dtype, 0, 0, m, n, k, lhs, rhs, act_out, 0, mode, e);
+    if (rc != SL_OK) return rc;
+    if (k == 0 && bias) {   // (gemm of an empty contraction clears the output and applies no epilogue)
+        const size_t total = m * n, cap = (size_t)ctx->num_sms * 8, blocks = (total + 255) / 256;
+        SL_LAUNCH(ctx, epilogue_pass_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, total, n, (float*)act_out, (const float*)bias, 0, (float*)nullptr,
+                  (const float*)nullptr);
+    }
+    const size_t nw = (n + 31) / 32, words = m * nw, cap = (size_t)ctx->num_sms * 8, blocks = (words + 255) / 256;
+    SL_LAUNCH(ctx, bits_relu_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, m, n, nw, (float*)act_out, mask_bits);
+    return SL_OK;
+}
+
+int sl_linear_bwd_input_relu_bits(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* rhs, const void* out_grad, const uint32_t* mask_bits,
+                                  void* x_grad, int mode) {
+    SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
+    SL_REQUIRE(ctx, dtype == SL_F32, "sl_linear_bwd_input_relu_bits is f32 only");
+    SL_REQUIRE(ctx, x_grad != nullptr && mask_bits != nullptr, "NULL argument");
+    if (m == 0 || k == 0) return SL_OK;
+    sl_note_writes(ctx, x_grad);
+    Epi e;
+    // x_grad[m x k] = out_grad[m x n] * rhs[k x n]^T: the product's output extent is k, its contraction n
+    const bool al4 = (reinterpret_cast<uintptr_t>(mask_bits) & 3u) == 0;
+    const bool skinny = n >= 1 && n <= 16 && k % 32 == 0 && al4 && (mode < 0 ? ctx->gemm_mode : mode) != SL_GEMM_SIMT;   // the kernel decides; checked below
+    if (n > 0 && bits_fused_path(ctx, mode, m, k, n, x_grad, nullptr, mask_bits)) {
+        e.bits_in = mask_bits;
+        return gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, x_grad, 0, mode, e);
+    }
+    if (skinny && !tc_eligible(m, k, n)) {
+        int done = 0;
+        int rc = sl_gemm_skinny_f32(ctx, 0, 1, m, k, n, (const float*)out_grad, (const float*)rhs, (float*)x_grad, 0, nullptr, &done, mask_bits);
+        if (rc < 0 || (rc == SL_OK && done)) return rc;
+        if (rc > 0) rc = gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, x_grad, 0, mode, e);   // not a skinny shape after all
+        if (rc != SL_OK) return rc;
+    } else {
+        int rc = gemm_ex_impl(ctx, dtype, 0, 1, m, k, n, out_grad, rhs, x_grad, 0, mode, e);
+        if (rc != SL_OK) return rc;
+    }
+    const size_t nw = (k + 31) / 32, total = m * k, cap = (size_t)ctx->num_sms * 8, blocks = (total + 255) / 256;
+    SL_LAUNCH(ctx, bits_apply_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, m, k, nw, (float*)x_grad, mask_bits);
+    return SL_OK;
 }
 
 int sl_add_row_mut_grad(sl_ctx* ctx, int dtype, size_t rows, size_t cols, void* rhs_grad, const void* out_grad);

@@ -159,9 +159,12 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
     const size_t L = layers_.size();
     const size_t oc = dims_.back();
     if (fused_batch_ != batch) {  // (re)allocate the persistent activations: z_l, a_l = relu(z_l), gz_l = d loss / d z_l
-        z_.clear(); a_.clear(); gz_.clear();
+        z_.clear(); a_.clear(); gz_.clear(); mbits_.clear();
         for (size_t l = 0; l < L; ++l) {
-            z_.push_back(d.buffer(batch * dims_[l + 1], SL_F32));
+            // hidden layers keep a_l = relu(z_l) and ONE BIT per element of (z_l >= 0) — all backward needs of z_l (the relu gradient,
+            // src/matrix.rs:181-188); the logits z_{L-1} of the last layer are kept whole for the softmax
+            z_.push_back(l + 1 == L ? d.buffer(batch * dims_[l + 1], SL_F32) : Buf());
+            mbits_.push_back(l + 1 == L ? Buf() : d.buffer(batch * ((dims_[l + 1] + 31) / 32), SL_I32));
             a_.push_back(d.buffer(batch * dims_[l + 1], SL_F32));
             gz_.push_back(d.buffer(batch * dims_[l + 1], SL_F32));
         }
@@ -183,9 +186,12 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
     // ---- forward: Linear + relu fused; the 10-class head goes through the skinny kernel + add_row_mut + softmax
     const void* in = x->dptr;
     for (size_t l = 0; l < L; ++l) {
-        const bool last = l + 1 == L;
-        d.check(sl_linear_fwd(c, SL_F32, batch, dims_[l], dims_[l + 1], in, layers_[l].weights.data->dptr, layers_[l].bias.data->dptr,
-                              z_[l]->dptr, last ? nullptr : a_[l]->dptr, -1));
+        if (l + 1 == L)
+            d.check(sl_linear_fwd(c, SL_F32, batch, dims_[l], dims_[l + 1], in, layers_[l].weights.data->dptr, layers_[l].bias.data->dptr,
+                                  z_[l]->dptr, nullptr, -1));
+        else
+            d.check(sl_linear_fwd_bits(c, SL_F32, batch, dims_[l], dims_[l + 1], in, layers_[l].weights.data->dptr, layers_[l].bias.data->dptr,
+                                       a_[l]->dptr, (uint32_t*)mbits_[l]->dptr, -1));
         in = a_[l]->dptr;
     }
     Buf out = a_[L - 1];
@@ -226,8 +232,8 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
         sgd_order_.push_back(li);
     };
     auto input_grad = [&](size_t li) {
-        d.check(sl_linear_bwd_input_relu(c, SL_F32, batch, dims_[li], dims_[li + 1], layers_[li].weights.data->dptr, gz_[li]->dptr, z_[li - 1]->dptr,
-                                         gz_[li - 1]->dptr, -1));
+        d.check(sl_linear_bwd_input_relu_bits(c, SL_F32, batch, dims_[li], dims_[li + 1], layers_[li].weights.data->dptr, gz_[li]->dptr,
+                                              (const uint32_t*)mbits_[li - 1]->dptr, gz_[li - 1]->dptr, -1));
     };
     sgd_order_.clear();
     if (order == 1) {

@@ -54,8 +54,8 @@ class Mlp {
     // Phases can be run separately so that a data-parallel driver can put the exchange between backward and sgd.
     StepResult forward_backward(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics);
     // The same step with the chains the tape exposes fused (what custos' `Lazy` graph + `optimize()` hook is for, nn.rs:302):
-    //   gemm -> add_row_mut -> relu            => one gemm with a bias + relu epilogue (sl_linear_fwd)
-    //   gemm_grad(lhs) -> relu grad            => one gemm with a relu-mask epilogue (sl_linear_bwd_input_relu)
+    //   gemm -> add_row_mut -> relu            => one gemm with a bias + relu epilogue that also emits the mask bits (sl_linear_fwd_bits)
+    //   gemm_grad(lhs) -> relu grad            => one gemm with a mask-bit epilogue (sl_linear_bwd_input_relu_bits)
     //   zero_grad of activation gradients      => dropped: every activation gradient is produced by a SET kernel
     // Every per-element operation and its order are those of the unfused step, so losses, gradients and weights are
     // bit-identical to forward_backward() (tests/test_gpu_mlp.py::test_fused_step_is_bit_identical).
@@ -101,7 +101,7 @@ class Mlp {
     std::vector<size_t> sgd_order_;      // layers in the order their exchanges were issued
     // persistent activations / activation gradients of the fused step (sized for the last batch seen)
     size_t fused_batch_ = 0;
-    std::vector<Buf> z_, a_, gz_;
+    std::vector<Buf> z_, a_, gz_, mbits_;   // (z_ only for the last layer; mbits_: relu mask bits of the hidden layers)
     Buf loss_tmp_[4];
     StepResult read_metrics(bool want);
 };

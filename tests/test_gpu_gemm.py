@@ -510,3 +510,48 @@ def test_plane_scope_sees_non_gemm_writes(mode, monkeypatch):
         assert np.array_equal(p, s), i
     assert np.all(plain[-1] == 0)
     ctx.close()
+
+
+@pytest.mark.parametrize("m,k,n", [(8192, 4096, 4096),    # 2-CTA kernel, bits in the epilogue (the MLP's shapes at 1/8 of the batch)
+                                   (4096, 16384, 4096),   # split-K: the fold kernel takes / applies the bits
+                                   (768, 512, 384),       # single-CTA tensor-core kernel: element-wise bit passes
+                                   (100, 70, 50),         # CUDA-core kernel, ragged width (partial last mask word)
+                                   (4096, 10, 4096),      # k = 10: forward through the skinny kn kernel
+                                   (3000, 4096, 10)])     # n = 10: the head; its input gradient runs the skinny nt kernel with fused bits
+@pytest.mark.parametrize("mode", ["3xf16", "3xtf32"])
+def test_linear_mask_bits_variants_are_bit_identical(m, k, n, mode, monkeypatch):
+    """sl_linear_fwd_bits / sl_linear_bwd_input_relu_bits (relu mask as one bit per element) against sl_linear_fwd /
+    sl_linear_bwd_input_relu (mask = the pre-activation matrix): same activations, same input gradients, bit for bit, and the
+    bits are exactly (z >= 0) — src/matrix.rs:181-188.  Default dispatch, every path the bits can take."""
+    import ctypes as C
+    import sliced_b200 as S
+    monkeypatch.delenv("SLICED_GEMM_TC_FORCE", raising=False)
+    ctx = S.Context(0)
+    L, md = ctx.lib, MODES[mode]
+    rng = np.random.default_rng(m + k + n)
+    x, w, bias = _rand32(rng, m * k, 0, 1), _rand32(rng, k * n, -0.05, 0.05), _rand32(rng, n, -0.5, 0.5)
+    if n >= 64:
+        bias[:7] = 0; w.reshape(k, n)[:, :7] = 0   # exact zeros in z: the mask's >= matters
+    dx, dw, db = ctx.array(x), ctx.array(w), ctx.array(bias)
+    z, a, a2 = ctx.empty(m * n), ctx.empty(m * n), ctx.empty(m * n)
+    nw = (n + 31) // 32
+    bits = ctx.zeros(m * nw, np.int32)
+    S.capi.check(ctx.h, L.sl_linear_fwd(ctx.h, S.F32, m, k, n, dx.ptr, dw.ptr, db.ptr, z.ptr, a.ptr, md))
+    S.capi.check(ctx.h, L.sl_linear_fwd_bits(ctx.h, S.F32, m, k, n, dx.ptr, dw.ptr, db.ptr, a2.ptr, bits.ptr, md))
+    zh = z.numpy().reshape(m, n)
+    assert np.array_equal(a.numpy().view(np.uint32), a2.numpy().view(np.uint32))
+    want = np.zeros((m, nw * 32), bool)
+    want[:, :n] = zh >= 0
+    want = np.packbits(want.reshape(m, nw, 32), axis=-1, bitorder="little").view(np.uint32).reshape(m, nw)
+    assert np.array_equal(bits.numpy().view(np.uint32).reshape(m, nw), want)
+    if n >= 64:
+        assert np.all(zh[:, :7] == 0) and np.all(want[:, 0] & 0x7F == 0x7F)
+    # input gradient of the NEXT layer's product through this relu: gx[m x n] = (z >= 0) * (g[m x p] W2[n x p]^T)
+    for p_out in (10, 256):
+        w2, g = _rand32(rng, n * p_out, -0.05, 0.05), _rand32(rng, m * p_out)
+        dw2, dg = ctx.array(w2), ctx.array(g)
+        gx, gx2 = ctx.empty(m * n), ctx.empty(m * n)
+        S.capi.check(ctx.h, L.sl_linear_bwd_input_relu(ctx.h, S.F32, m, n, p_out, dw2.ptr, dg.ptr, z.ptr, gx.ptr, md))
+        S.capi.check(ctx.h, L.sl_linear_bwd_input_relu_bits(ctx.h, S.F32, m, n, p_out, dw2.ptr, dg.ptr, bits.ptr, gx2.ptr, md))
+        assert np.array_equal(gx.numpy().view(np.uint32), gx2.numpy().view(np.uint32)), p_out
+    ctx.close()
