@@ -246,6 +246,10 @@ def run_ours(args):
 
     mlp = Mlp(dev, DIMS, 0)
     mlp.set_fused(not args.unfused)
+    # data-parallel runs pipeline each layer's gradient join + SGD update into the next step's forward pass (bit-identical; see
+    # Mlp::set_deferred); every timed region below ends with mlp.flush(), so all of its updates are inside it.  SLICED_DP_DEFERRED=0: off
+    deferred = world > 1 and not args.unfused and os.environ.get("SLICED_DP_DEFERRED", "1") != "0"
+    mlp.set_deferred(deferred)
     W, B = make_params()  # identical seeded init on every rank (replicas stay bit-identical: same summed gradients)
     for l in range(len(DIMS) - 1):
         mlp.weights(l).write(W[l])
@@ -340,6 +344,7 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         resident_step(False)   # loss / accuracy are still computed on the device every step; only the host read is outside `value`
+    mlp.flush()
     e1.record(stream)
     torch.cuda.synchronize()
     sampler.mark_end()
@@ -390,6 +395,7 @@ def run_ours(args):
     barrier()
     e0.record(stream)
     e2e_run(args.steps)
+    mlp.flush()
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
@@ -408,6 +414,7 @@ def run_ours(args):
         b0.record(stream)
         for _ in range(bsteps):
             resident_step(False)
+        mlp.flush()
         b1.record(stream)
         torch.cuda.synchronize()
         capi.check(ctx, lib.sl_ctx_profile_report(ctx, buf, len(buf)))
@@ -467,7 +474,7 @@ def run_ours(args):
                     higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=WORKLOAD if not args.debug_per_gpu_batch else "DIAGNOSIS RUN (per-GPU batch overridden): " + WORKLOAD,
                                 global_batch=global_batch, per_gpu_batch=batch, parallelism=f"dp{world}",
-                                gemm_mode=args.gemm_mode, fused_epilogues=not args.unfused, l2="inputs (>= 128 MiB per operand at every N) exceed the 126 MB L2; no flush needed"),
+                                gemm_mode=args.gemm_mode, fused_epilogues=not args.unfused, dp_pipelined_update=bool(deferred), l2="inputs (>= 128 MiB per operand at every N) exceed the 126 MB L2; no flush needed"),
                     e2e=dict(value=global_batch / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline,
                     training=dict(first_step_mean_loss=first_loss, last_step_mean_loss=loss_sum / batch, last_step_accuracy=correct / batch,

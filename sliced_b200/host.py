@@ -74,6 +74,8 @@ def _lib():
             "slh_mlp_params": ([_vp], _vp),
             "slh_mlp_forward_backward": ([_vp, _vp, _vp, _vp, _sz, _sz, _i, P(_d), P(C.c_longlong)], _i),
             "slh_mlp_set_fused": ([_vp, _i], None),
+            "slh_mlp_set_deferred": ([_vp, _i], _i),
+            "slh_mlp_flush": ([_vp], _i),
             "slh_mlp_allreduce_grads": ([_vp], _i),
             "slh_mlp_sgd": ([_vp, _d], _i),
             "slh_mlp_step": ([_vp, _vp, _vp, _vp, _sz, _sz, _d, _i, P(_d), P(C.c_longlong)], _i),
@@ -352,6 +354,10 @@ class Mlp:
         return loss.value, correct.value
 
     def set_fused(self, on: bool): _lib().slh_mlp_set_fused(self.h, int(on))
+    def set_deferred(self, on: bool):
+        """data-parallel pipelining across steps: each layer's gradient join + SGD update moves into the next forward pass (flush() applies what is owed)"""
+        _chk(_lib().slh_mlp_set_deferred(self.h, int(on)))
+    def flush(self): _chk(_lib().slh_mlp_flush(self.h))
     def allreduce_grads(self): _chk(_lib().slh_mlp_allreduce_grads(self.h))
     def sgd(self, lr): _chk(_lib().slh_mlp_sgd(self.h, lr))
 

@@ -162,10 +162,10 @@ slh_mlp* slh_mlp_new(slh_device* d, int n_dims, const size_t* dims, int loss_kin
 void slh_mlp_free(slh_mlp* m) { delete (Mlp*)m; }
 size_t slh_mlp_n_params(slh_mlp* m) { return ((Mlp*)m)->n_params(); }
 void* slh_mlp_metrics_dptr(slh_mlp* m) { return ((Mlp*)m)->metrics_dptr(); }
-slh_buffer* slh_mlp_weights(slh_mlp* m, int layer) { return (slh_buffer*)wrap_handle(((Mlp*)m)->layer(layer).weights.data); }
-slh_buffer* slh_mlp_bias(slh_mlp* m, int layer) { return (slh_buffer*)wrap_handle(((Mlp*)m)->layer(layer).bias.data); }
-slh_buffer* slh_mlp_grad_bucket(slh_mlp* m) { return (slh_buffer*)wrap_handle(((Mlp*)m)->grad_bucket()); }
-slh_buffer* slh_mlp_params(slh_mlp* m) { return (slh_buffer*)wrap_handle(((Mlp*)m)->params()); }
+slh_buffer* slh_mlp_weights(slh_mlp* m, int layer) { return guard([&]() { ((Mlp*)m)->flush(); return (slh_buffer*)wrap_handle(((Mlp*)m)->layer(layer).weights.data); }, (slh_buffer*)nullptr); }
+slh_buffer* slh_mlp_bias(slh_mlp* m, int layer) { return guard([&]() { ((Mlp*)m)->flush(); return (slh_buffer*)wrap_handle(((Mlp*)m)->layer(layer).bias.data); }, (slh_buffer*)nullptr); }
+slh_buffer* slh_mlp_grad_bucket(slh_mlp* m) { return guard([&]() { ((Mlp*)m)->flush(); return (slh_buffer*)wrap_handle(((Mlp*)m)->grad_bucket()); }, (slh_buffer*)nullptr); }
+slh_buffer* slh_mlp_params(slh_mlp* m) { return guard([&]() { ((Mlp*)m)->flush(); return (slh_buffer*)wrap_handle(((Mlp*)m)->params()); }, (slh_buffer*)nullptr); }
 
 int slh_mlp_forward_backward(slh_mlp* m, slh_buffer* x, slh_buffer* y, slh_buffer* labels, size_t batch, size_t grad_rows, int want_metrics,
                              double* loss_sum, long long* correct) {
@@ -180,6 +180,8 @@ int slh_mlp_forward_backward(slh_mlp* m, slh_buffer* x, slh_buffer* y, slh_buffe
     }, -1);
 }
 void slh_mlp_set_fused(slh_mlp* m, int on) { ((Mlp*)m)->set_fused(on != 0); }
+int slh_mlp_set_deferred(slh_mlp* m, int on) { return guard([&]() { ((Mlp*)m)->set_deferred(on != 0); return 0; }, -1); }
+int slh_mlp_flush(slh_mlp* m) { return guard([&]() { ((Mlp*)m)->flush(); return 0; }, -1); }
 int slh_mlp_allreduce_grads(slh_mlp* m) { return guard([&]() { ((Mlp*)m)->allreduce_grads(); return 0; }, -1); }
 int slh_mlp_sgd(slh_mlp* m, double lr) { return guard([&]() { ((Mlp*)m)->sgd(lr); return 0; }, -1); }
 int slh_mlp_step(slh_mlp* m, slh_buffer* x, slh_buffer* y, slh_buffer* labels, size_t batch, size_t grad_rows, double lr, int want_metrics,

@@ -49,6 +49,7 @@ bool Mlp::small_active(size_t batch) const {
 }
 
 StepResult Mlp::step_small(const Buf& x, const Buf& y, size_t batch, double lr, bool want_metrics) {
+    flush();
     dev_.flush_pending();
     dev_.check(sl_mlp_small_step(dev_.ctx(), SL_F32, (int)layers_.size(), dims_.data(), seg_off_.data(), batch, x->dptr, y->dptr, params_->dptr,
                                  bucket_->dptr, lr, metrics_dev_));
@@ -56,11 +57,14 @@ StepResult Mlp::step_small(const Buf& x, const Buf& y, size_t batch, double lr, 
 }
 
 Mlp::~Mlp() {
+    try { flush(); } catch (...) {}
     if (graph_) sl_graph_destroy(dev_.ctx(), graph_);
     if (metrics_dev_) sl_free(dev_.ctx(), metrics_dev_);
 }
 
 StepResult Mlp::step_replay(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, double lr, bool want_metrics) {
+    if (deferred_active()) throw Error(SL_ERR_INVALID_ARG, "Mlp::step_replay: a deferred (cross-step pipelined) data-parallel step cannot be captured");
+    flush();
     const GraphKey key{x->dptr, y->dptr, labels ? labels->dptr : nullptr, batch, grad_rows, lr, fused_};
     const bool same = graph_ && key.x == gkey_.x && key.y == gkey_.y && key.l == gkey_.l && key.batch == gkey_.batch &&
                       key.rows == gkey_.rows && key.lr == gkey_.lr && key.fused == gkey_.fused;
@@ -92,6 +96,7 @@ StepResult Mlp::step_replay(const Buf& x, const Buf& y, const Buf& labels, size_
 }
 
 StepResult Mlp::forward_backward(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics) {
+    flush();
     Device& d = dev_;
     const size_t L = layers_.size();
     const size_t out_cols = dims_.back();
@@ -171,9 +176,6 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
         loss_tmp_[1] = d.buffer(batch, SL_F32);       // per-sample loss
         fused_batch_ = batch;
     }
-    // parameter gradients accumulate (bias: += column sums) -> zero the bucket; activation gradients are all SET
-    for (size_t l = 0; l < L; ++l)   // (the weight gradients are SET by their gemm; the padding between segments is never written)
-        d.check(sl_clear(c, (float*)bucket_->dptr + seg_off_[2 * l + 1], (seg_off_[2 * l + 2] - seg_off_[2 * l + 1]) * sizeof(float)));
     d.check(sl_clear(c, metrics_dev_, 16));
     // every activation / weight / gz buffer is read by two gemms of this step (forward + a gradient gemm): split each into its
     // TF32 planes once.  Nothing but gemms writes those buffers between here and the end of the backward pass.
@@ -186,6 +188,11 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
     // ---- forward: Linear + relu fused; the 10-class head goes through the skinny kernel + add_row_mut + softmax
     const void* in = x->dptr;
     for (size_t l = 0; l < L; ++l) {
+        // deferred data-parallel mode: the previous step's join + SGD update of this layer, right before its weights are used
+        if (have_pending_ && pending_[l]) apply_pending_layer(l);
+        // parameter gradients accumulate (bias: += column sums) -> zero that segment of the bucket (the weight gradients are SET by
+        // their gemm; the padding between segments is never written); activation gradients are all SET
+        d.check(sl_clear(c, (float*)bucket_->dptr + seg_off_[2 * l + 1], (seg_off_[2 * l + 2] - seg_off_[2 * l + 1]) * sizeof(float)));
         if (l + 1 == L)
             d.check(sl_linear_fwd(c, SL_F32, batch, dims_[l], dims_[l + 1], in, layers_[l].weights.data->dptr, layers_[l].bias.data->dptr,
                                   z_[l]->dptr, nullptr, -1));
@@ -193,6 +200,11 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
             d.check(sl_linear_fwd_bits(c, SL_F32, batch, dims_[l], dims_[l + 1], in, layers_[l].weights.data->dptr, layers_[l].bias.data->dptr,
                                        a_[l]->dptr, (uint32_t*)mbits_[l]->dptr, -1));
         in = a_[l]->dptr;
+    }
+    if (have_pending_) {   // every owed update has been applied: join the communication stream before new exchanges are issued
+        d.check(sl_comm_wait(c));
+        exchanged_ = false;
+        have_pending_ = false;
     }
     Buf out = a_[L - 1];
     // softmax -> accuracy -> cce -> cce_grad -> softmax_grad (nn.rs:190-233: nine launches over batch x 10 on the tape path) as ONE
@@ -211,7 +223,7 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
     //                      up (the exchanges of the early ones hide behind the later gemms)
     const int dp_chunks = env_int("SLICED_DP_CHUNKS", 1);
     const bool chunk_all = env_int("SLICED_DP_CHUNKS_ALL", 0) != 0;
-    const int order = env_int("SLICED_DP_ORDER", 0);
+    const int order = env_int("SLICED_DP_ORDER", deferred_active() ? 1 : 0);
     layer_exchanges_.assign(L, 0);
     auto params_grad = [&](size_t li, bool last) {
         const size_t I = dims_[li], O = dims_[li + 1];
@@ -251,8 +263,34 @@ StepResult Mlp::forward_backward_fused(const Buf& x, const Buf& y, const Buf& la
 
 // Join of the per-layer exchanges and the SGD step, layer by layer in the order the exchanges were issued: the update of a layer
 // whose summed gradients have arrived overlaps the exchanges still in flight (element-wise: identical to one flat sgd()).
+bool Mlp::deferred_active() const { return deferred_ && fused_active() && sl_comm_nranks(dev_.ctx()) > 1; }
+
+void Mlp::apply_pending_layer(size_t li) {
+    sl_ctx* c = dev_.ctx();
+    dev_.check(sl_comm_wait_n(c, layer_exchanges_[li]));
+    const size_t off = seg_off_[2 * li], n = seg_off_[2 * li + 2] - off;
+    dev_.check(sl_sgd_step(c, SL_F32, (float*)params_->dptr + off, (float*)bucket_->dptr + off, pending_lr_, n));
+    pending_[li] = 0;
+}
+
+void Mlp::flush() {
+    if (!have_pending_) return;
+    for (size_t li : sgd_order_)
+        if (pending_[li]) apply_pending_layer(li);
+    dev_.check(sl_comm_wait(dev_.ctx()));
+    exchanged_ = false;
+    have_pending_ = false;
+}
+
 void Mlp::exchange_and_sgd(double lr) {
     sl_ctx* c = dev_.ctx();
+    if (exchanged_ && deferred_active()) {   // owed to the next forward pass (or flush())
+        pending_.assign(layers_.size(), 0);
+        for (size_t li : sgd_order_) pending_[li] = 1;
+        pending_lr_ = lr;
+        have_pending_ = true;
+        return;
+    }
     if (!exchanged_ || sl_comm_nranks(c) <= 1 || !env_int("SLICED_DP_LAYER_SGD", 1)) {
         allreduce_grads();
         sgd(lr);
@@ -268,6 +306,7 @@ void Mlp::exchange_and_sgd(double lr) {
 }
 
 void Mlp::allreduce_grads() {
+    flush();
     if (exchanged_) {  // the fused backward already issued per-layer exchanges: just join the communication stream
         dev_.check(sl_comm_wait(dev_.ctx()));
         exchanged_ = false;
@@ -277,11 +316,13 @@ void Mlp::allreduce_grads() {
 }
 
 void Mlp::sgd(double lr) {
+    flush();
     // SGD::step over lin1..lin3 params (nn.rs:235-237): parameters and gradients are both flat -> one kernel
     dev_.check(sl_sgd_step(dev_.ctx(), SL_F32, params_->dptr, bucket_->dptr, lr, n_params_));
 }
 
 Matrix Mlp::predict(const Buf& x, size_t batch) {
+    flush();
     dev_.set_tape_enabled(false);
     Matrix out(x, batch, dims_[0]);
     for (size_t l = 0; l < layers_.size(); ++l) {

@@ -60,7 +60,16 @@ class Mlp {
     // Every per-element operation and its order are those of the unfused step, so losses, gradients and weights are
     // bit-identical to forward_backward() (tests/test_gpu_mlp.py::test_fused_step_is_bit_identical).
     StepResult forward_backward_fused(const Buf& x, const Buf& y, const Buf& labels, size_t batch, size_t grad_rows, bool want_metrics);
-    void set_fused(bool on) { fused_ = on; }
+    // Data-parallel pipelining across steps (fused step with a communicator only; default off).  The gradient exchange of the weight
+    // gradient computed LAST in backward has nothing left in its own step to hide behind.  Deferred mode (a) orders backward as the
+    // dX chain first, then the weight gradients from the input layer up, so that the exposed exchange belongs to a late layer, and
+    // (b) moves every layer's join + SGD update from the end of the step into the NEXT forward pass, right before that layer's gemm:
+    // the late layers' exchanges then overlap the next step's input upload, operand split and first gemms.  Same arithmetic in the
+    // same order on every parameter (update before use), so results are bit-identical; parameters are only current after flush()
+    // (every accessor of the C bridge, predict(), forward_backward(), sgd() and allreduce_grads() flush first).
+    void set_deferred(bool on) { flush(); deferred_ = on; }
+    void flush();
+    void set_fused(bool on) { flush(); fused_ = on; }
     bool fused() const { return fused_; }
     bool fused_active() const { return fused_ && loss_ == LOSS_SOFTMAX_CCE; }
     void allreduce_grads();          // sl_allreduce_sum over the bucket (no-op for a world of one)
@@ -94,6 +103,12 @@ class Mlp {
     void* metrics_dev_ = nullptr;  // [loss_sum f32][correct i32]
     bool fused_ = false;
     bool exchanged_ = false;          // per-layer async all-reduces are in flight (fused backward)
+    bool deferred_ = false;           // set_deferred
+    bool have_pending_ = false;       // deferred mode: joins + SGD updates of the previous step are still owed
+    double pending_lr_ = 0;
+    std::vector<char> pending_;       // per layer
+    bool deferred_active() const;
+    void apply_pending_layer(size_t li);
     void* graph_ = nullptr;           // captured step (step_replay)
     struct GraphKey { const void *x, *y, *l; size_t batch, rows; double lr; bool fused; } gkey_{};
     std::vector<size_t> seg_off_;

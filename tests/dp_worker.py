@@ -41,6 +41,7 @@ def main(out_path, dims, batch, steps, lr):
     dev = CUDA(local, cached=True)
     dp.init_comm(capi.load(), dev.ctx_handle, dist, rank, world)
     mlp = make(dev)
+    mlp.set_deferred(os.environ.get("SLICED_TEST_DEFERRED", "0") == "1")   # cross-step pipelined join + SGD (Mlp::set_deferred)
     dx, dy, dl = dev.buffer(x[lo:hi]).no_grad(), dev.buffer(y[lo:hi]).no_grad(), dev.buffer(labels[lo:hi])
     # step 1 in two phases so that the summed bucket can be read before SGD consumes it
     l0, c0 = mlp.forward_backward(dx, dy, dl, hi - lo, grad_rows=batch)
@@ -89,7 +90,7 @@ def main(out_path, dims, batch, steps, lr):
                    one_gpu_bucket_rel_diff_vs_oracle=float(np.max(np.abs(bucket1 - bucket_o))) / gmax,
                    params_rel_diff_vs_one_gpu=float(np.max(np.abs(params - params1))) / float(np.max(np.abs(params1))),
                    params_rel_diff_vs_oracle=float(np.max(np.abs(params - flat_o))) / float(np.max(np.abs(flat_o))),
-                   crc_identical_across_ranks=all(int(c.item()) == crc for c in allc),
+                   crc_identical_across_ranks=all(int(c.item()) == crc for c in allc), params_crc=crc,
                    loss_dp=[float(v) for v in m[:, 0].cpu()], correct_dp=[int(v) for v in m[:, 1].cpu()],
                    loss_oracle=[float(h[0]) for h in ho], correct_oracle=[int(h[1]) for h in ho])
         del m1, fx, fy, fl
