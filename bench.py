@@ -77,6 +77,32 @@ def ncu_traffic():
         return None
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Run this rank's host threads on the NUMA node its GPU hangs off (sysfs), so that pinned host buffers are allocated there and
+    host->device copies do not cross sockets (8 ranks uploading 1 GB per step otherwise share one inter-socket link).  Returns the
+    node, or None when the topology cannot be read (then nothing is changed).  SLICED_BENCH_NUMA=0 switches it off."""
+    if os.environ.get("SLICED_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -216,6 +242,8 @@ def run_ours(args):
     if args.gpus > 1 and world == 1:
         raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local_rank)
+    # (multi-GPU runs only: at N=1 nothing competes for the host links, and the CPU-baseline leg keeps all host cores)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # before any pinned allocation: first touch on that node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -474,7 +502,7 @@ def run_ours(args):
                     higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=WORKLOAD if not args.debug_per_gpu_batch else "DIAGNOSIS RUN (per-GPU batch overridden): " + WORKLOAD,
                                 global_batch=global_batch, per_gpu_batch=batch, parallelism=f"dp{world}",
-                                gemm_mode=args.gemm_mode, fused_epilogues=not args.unfused, dp_pipelined_update=bool(deferred), l2="inputs (>= 128 MiB per operand at every N) exceed the 126 MB L2; no flush needed"),
+                                gemm_mode=args.gemm_mode, fused_epilogues=not args.unfused, dp_pipelined_update=bool(deferred), host_numa_node=numa, l2="inputs (>= 128 MiB per operand at every N) exceed the 126 MB L2; no flush needed"),
                     e2e=dict(value=global_batch / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline,
                     training=dict(first_step_mean_loss=first_loss, last_step_mean_loss=loss_sum / batch, last_step_accuracy=correct / batch,
