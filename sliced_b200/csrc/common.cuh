@@ -34,11 +34,12 @@ struct sl_ctx {
     std::vector<PlaneEntry> plane_cache;
     size_t plane_cursor = 0;
     bool plane_scope = false;
-    // per-column power-of-two scales of a buffer, a by-product of splitting it row-wise (3xFP16 mode), reused inside the scope
-    struct ColScale { const void* src; size_t rows, cols; float* scale; float* inv; size_t cap; bool valid; };
-    std::vector<ColScale> colscale_cache;
-    size_t colscale_cursor = 0;
-    std::vector<const void*> cols_split_done;   // buffers already split column-wise in this scope
+    // 3xFP16 planes of a K-contiguous operand [rows x cols] (scaled per ROW), kept inside a scope: a later gemm of the scope that
+    // contracts over the ROWS of the same buffer consumes them as its MN-major operand and folds the row scales into the other
+    // operand's split instead of splitting this buffer a second time per column
+    struct RowPlanes { const void* src; size_t rows, cols; void* hi; void* lo; float* inv; size_t cap_bytes, cap_rows; bool valid; };
+    std::vector<RowPlanes> rowplane_cache;
+    size_t rowplane_cursor = 0;
     // second stream for host->device prefetch (sl_write_prefetch), created lazily
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_done = nullptr, compute_done = nullptr;
@@ -62,10 +63,8 @@ static inline void sl_note_write(sl_ctx* ctx, const void* p) {
     const char* q = (const char*)p;
     for (auto& e : ctx->plane_cache)
         if (e.valid && q >= (const char*)e.src && q < (const char*)e.src + e.elems * 4) e.valid = false;
-    for (auto& e : ctx->colscale_cache)
+    for (auto& e : ctx->rowplane_cache)
         if (e.valid && q >= (const char*)e.src && q < (const char*)e.src + e.rows * e.cols * 4) e.valid = false;
-    for (auto& d : ctx->cols_split_done)
-        if (d == p) d = nullptr;
 }
 template <typename... P>
 static inline void sl_note_writes(sl_ctx* ctx, P... ptrs) {

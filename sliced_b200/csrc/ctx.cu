@@ -120,8 +120,11 @@ int sl_ctx_destroy(sl_ctx* ctx) {
         if (e.hi) cudaFree(e.hi);
         if (e.lo) cudaFree(e.lo);
     }
-    for (auto& e : ctx->colscale_cache)
-        if (e.scale) cudaFree(e.scale);
+    for (auto& e : ctx->rowplane_cache) {
+        if (e.hi) cudaFree(e.hi);
+        if (e.lo) cudaFree(e.lo);
+        if (e.inv) cudaFree(e.inv);
+    }
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ws2) cudaFree(ctx->ws2);
     if (ctx->copy_stream) {

@@ -231,6 +231,8 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, float* crow
     if (p.col_scale) {
         const float4 cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0));
         v.x = (v.x * rs) * cs.x; v.y = (v.y * rs) * cs.y; v.z = (v.z * rs) * cs.z; v.w = (v.w * rs) * cs.w;
+    } else if (p.row_scale) {
+        v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
     }
     if (p.accumulate) {
         const float4 o = *reinterpret_cast<const float4*>(crow + n0);
@@ -259,6 +261,7 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, float* crow
 }
 __device__ __forceinline__ void epilogue_store1(const GemmParams& p, float* crow, size_t row_off, int n, float v, float rs = 1.f) {
     if (p.col_scale) v = (v * rs) * __ldg(p.col_scale + n);
+    else if (p.row_scale) v *= rs;
     if (p.accumulate) v += crow[n];
     if (p.bias) v += __ldg(p.bias + n);
     if (p.mask_src) v = (__ldg(p.mask_src + row_off + n) >= 0.f ? 1.f : 0.f) * v;
@@ -997,6 +1000,9 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                                 v[j] = (v[j] * rs) * cs.x; v[j + 1] = (v[j + 1] * rs) * cs.y;
                                 v[j + 2] = (v[j + 2] * rs) * cs.z; v[j + 3] = (v[j + 3] * rs) * cs.w;
                             }
+                    } else if (p.row_scale) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= rs;
                     }
                     if (p.accumulate) epi_gather<false>(stage, lane, v, cbase + n0, (size_t)p.N, rows_valid, cols_valid);
                     if (p.bias) {
@@ -1171,18 +1177,13 @@ __device__ __forceinline__ void split4_store(const float4& v, float sx, float sy
 // K-contiguous operand [R x K] (K % 4 == 0): one 128-thread block per row, several blocks resident per SM so that one row's
 // load latency hides behind the others' reductions and stores.  VPT float4 per thread hold a row of up to 512 * VPT elements in
 // registers between the max pass and the split pass (one HBM read); VPT = 0: longer rows, re-read (L2).
-// COLMAX: also keep max |x| per column over the rows this block handled -> colmax_partial[gridDim.x][K]: the column scales the same
-// buffer needs when a later gemm contracts over its rows instead (weight-gradient gemm).
-template <int VPT, bool COLMAX>
+template <int VPT>
 __global__ void __launch_bounds__(128) prep16_rows_kernel(size_t R, size_t K, const float* __restrict__ src, __half* __restrict__ hi,
-                                                          __half* __restrict__ lo, float* __restrict__ scale_inv, float* __restrict__ colmax_partial) {
+                                                          __half* __restrict__ lo, float* __restrict__ scale_inv) {
     constexpr int NV = VPT > 0 ? VPT : 1;
     __shared__ float red[4];
     __shared__ float bcast;
     const size_t nv = K / 4;
-    float4 cm[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) cm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (size_t row = blockIdx.x; row < R; row += gridDim.x) {
         const float4* s4 = reinterpret_cast<const float4*>(src + row * K);
         float4 v[NV];
@@ -1195,10 +1196,6 @@ __global__ void __launch_bounds__(128) prep16_rows_kernel(size_t R, size_t K, co
                     const Pack<float> p = ld_stream(src + row * K + idx * 4);
                     v[i] = make_float4(p.v[0], p.v[1], p.v[2], p.v[3]);
                     m = absmax4(m, v[i]);
-                    if (COLMAX) {
-                        cm[i].x = fmaxf(cm[i].x, fabsf(v[i].x)); cm[i].y = fmaxf(cm[i].y, fabsf(v[i].y));
-                        cm[i].z = fmaxf(cm[i].z, fabsf(v[i].z)); cm[i].w = fmaxf(cm[i].w, fabsf(v[i].w));
-                    }
                 }
             }
         } else {
@@ -1229,20 +1226,15 @@ __global__ void __launch_bounds__(128) prep16_rows_kernel(size_t R, size_t K, co
         }
         // (the next iteration's first __syncthreads orders this row's read of `bcast` before the next write)
     }
-    if (COLMAX && VPT > 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const size_t idx = threadIdx.x + (size_t)i * 128;
-            if (idx < nv) *reinterpret_cast<float4*>(colmax_partial + (size_t)blockIdx.x * K + idx * 4) = cm[i];
-        }
-    }
 }
 
 // MN-contiguous operand [K x R] (R % 4 == 0), scale per column r over all K rows.
 // pass 1: grid (column blocks of 1024, slabs of rows) -> partial[slab][R] = max |x| over the slab
 // partial_sum (optional): the same pass also produces the slab's column SUMS (sl_linear_bwd_params: bias gradient).
+// row_factor (optional, [K], exact powers of two): the maxima are those of src[k][r] * row_factor[k] (the sums stay those of src)
 __global__ void __launch_bounds__(256) prep16_colmax_kernel(size_t K, size_t R, size_t rows_per_slab, const float* __restrict__ src,
-                                                            float* __restrict__ partial, float* __restrict__ partial_sum) {
+                                                            float* __restrict__ partial, float* __restrict__ partial_sum,
+                                                            const float* __restrict__ row_factor) {
     const size_t c = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
     if (c >= R) return;
     const size_t k0 = (size_t)blockIdx.y * rows_per_slab;
@@ -1251,7 +1243,8 @@ __global__ void __launch_bounds__(256) prep16_colmax_kernel(size_t K, size_t R, 
 #pragma unroll 4
     for (size_t k = k0; k < k1; ++k) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(src + k * R + c));
-        m.x = fmaxf(m.x, fabsf(v.x)); m.y = fmaxf(m.y, fabsf(v.y)); m.z = fmaxf(m.z, fabsf(v.z)); m.w = fmaxf(m.w, fabsf(v.w));
+        const float f = row_factor ? __ldg(row_factor + k) : 1.f;
+        m.x = fmaxf(m.x, fabsf(v.x * f)); m.y = fmaxf(m.y, fabsf(v.y * f)); m.z = fmaxf(m.z, fabsf(v.z * f)); m.w = fmaxf(m.w, fabsf(v.w * f));
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
     }
     *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * R + c) = m;
@@ -1290,14 +1283,15 @@ __global__ void __launch_bounds__(256) prep16_colscale_kernel(size_t R, int slab
 }
 // pass 3: element-wise split with the column's scale (planes keep the [K x R] layout)
 __global__ void __launch_bounds__(256) prep16_cols_kernel(size_t K, size_t R, const float* __restrict__ src, const float* __restrict__ scale,
-                                                          __half* __restrict__ hi, __half* __restrict__ lo) {
+                                                          __half* __restrict__ hi, __half* __restrict__ lo, const float* __restrict__ row_factor) {
     const size_t rv = R / 4;
     const size_t total = K * rv;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t c = (i % rv) * 4;
         const Pack<float> x = ld_stream(src + i * 4);
         const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
-        split4_store(make_float4(x.v[0], x.v[1], x.v[2], x.v[3]), sc.x, sc.y, sc.z, sc.w, hi + i * 4, lo + i * 4);
+        const float f = row_factor ? __ldg(row_factor + i / rv) : 1.f;   // (both factors are powers of two: x * f is exact)
+        split4_store(make_float4(x.v[0] * f, x.v[1] * f, x.v[2] * f, x.v[3] * f), sc.x, sc.y, sc.z, sc.w, hi + i * 4, lo + i * 4);
     }
 }
 
@@ -1720,72 +1714,27 @@ __global__ void __launch_bounds__(256) epilogue_pass_kernel(size_t total, size_t
     }
 }
 
-// Column-scale reuse inside a gemm scope: when a [rows x cols] buffer is split with its ROWS as the output index (contraction over
-// the columns), the same pass also yields max |x| per COLUMN for free; those are exactly the scales the buffer needs when a later
-// gemm of the scope contracts over its rows instead (activation: forward gemm, then weight-gradient gemm).
-static sl_ctx::ColScale* colscale_find(sl_ctx* ctx, const void* src, size_t rows, size_t cols) {
-    for (auto& e : ctx->colscale_cache)
-        if (e.valid && e.src == src && e.rows == rows && e.cols == cols) return &e;
-    return nullptr;
-}
-static int colscale_new(sl_ctx* ctx, const void* src, size_t rows, size_t cols, sl_ctx::ColScale** out) {
-    if (ctx->colscale_cursor >= ctx->colscale_cache.size()) ctx->colscale_cache.push_back(sl_ctx::ColScale{nullptr, 0, 0, nullptr, nullptr, 0, false});
-    sl_ctx::ColScale& e = ctx->colscale_cache[ctx->colscale_cursor++];
-    if (e.cap < cols) {
-        SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (e.scale) cudaFree(e.scale);
-        e.scale = nullptr;
-        SL_CUDA(ctx, cudaMalloc((void**)&e.scale, 2 * cols * sizeof(float)));
-        e.cap = cols;
-    }
-    e.inv = e.scale + cols;
-    e.src = src; e.rows = rows; e.cols = cols; e.valid = true;
-    *out = &e;
-    return SL_OK;
-}
-
 // 3xFP16 path: scale + split both operands into fp16 hi / lo planes IN THEIR OWN LAYOUT (K-major or MN-major, never transposed)
 // and run the kind::f16 2-CTA kernel; the epilogue undoes the scaling.
 // *inv_out receives the [mn] vector of inverse scales the epilogue needs (scale_inv, or a cached one).
 // colsum_acc (MN-major operand only): colsum_acc[j] += sum over k of src[k][j], computed in the same pass as the column maxima.
 static int prep16_operand(sl_ctx* ctx, const float* src, size_t mn, size_t k, bool k_contiguous, __half* hi, __half* lo, float* scale,
-                          float* scale_inv, const float** inv_out, float* colsum_acc) {
+                          float* scale_inv, const float** inv_out, float* colsum_acc, const float* row_factor = nullptr) {
     const size_t cap = (size_t)ctx->num_sms * 8;
     *inv_out = scale_inv;
     if (k_contiguous) {  // [mn x k]
-        bool seen_cols = false;   // this buffer was already split column-wise in this scope: nobody will ask for its column scales again
-        for (const void* q : ctx->cols_split_done) seen_cols |= (q == (const void*)src);
-        const bool want_colmax = ctx->plane_scope && k <= 8192 && mn >= 4 * cap && !seen_cols && !colscale_find(ctx, src, mn, k);
-        const unsigned grid = (unsigned)(want_colmax ? cap : (mn < cap * 8 ? mn : cap * 8));
-        float* partial = nullptr;
-        sl_ctx::ColScale* e = nullptr;
-        if (want_colmax) {
-            int rc = sl_ws_reserve(ctx, (size_t)grid * k * sizeof(float), (void**)&partial);
-            if (rc != SL_OK) return rc;
-            if ((rc = colscale_new(ctx, src, mn, k, &e)) != SL_OK) return rc;
-        }
-#define SL_ROWS(VPTV)                                                                                                                       \
-    do {                                                                                                                                    \
-        if (want_colmax) SL_LAUNCH(ctx, (prep16_rows_kernel<VPTV, true>), grid, 128, 0, mn, k, src, hi, lo, scale_inv, partial);             \
-        else SL_LAUNCH(ctx, (prep16_rows_kernel<VPTV, false>), grid, 128, 0, mn, k, src, hi, lo, scale_inv, (float*)nullptr);               \
-    } while (0)
+        const unsigned grid = (unsigned)(mn < cap * 8 ? mn : cap * 8);
+#define SL_ROWS(VPTV) SL_LAUNCH(ctx, (prep16_rows_kernel<VPTV>), grid, 128, 0, mn, k, src, hi, lo, scale_inv)
         if (k <= 2048) SL_ROWS(4);
         else if (k <= 4096) SL_ROWS(8);
         else if (k <= 8192) SL_ROWS(16);
-        else SL_LAUNCH(ctx, (prep16_rows_kernel<0, false>), grid, 128, 0, mn, k, src, hi, lo, scale_inv, (float*)nullptr);
+        else SL_ROWS(0);
 #undef SL_ROWS
-        if (want_colmax)
-            SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((k + 31) / 32), dim3(32, 8, 1), 0, k, (int)grid, (const float*)partial, e->scale, e->inv,
-                      (const float*)nullptr, (float*)nullptr);
         return SL_OK;
     }
-    // [k x mn]: column maxima in two deterministic passes (or from the scope cache), then the element-wise split
-    const float* use_scale = scale;
-    sl_ctx::ColScale* hit = (ctx->plane_scope && !colsum_acc) ? colscale_find(ctx, src, k, mn) : nullptr;
-    if (hit) {
-        use_scale = hit->scale;
-        *inv_out = hit->inv;
-    } else {
+    // [k x mn]: column maxima in two deterministic passes, then the element-wise split.
+    // row_factor: the buffer is split as src[k][mn] * row_factor[k] (the other operand's row scales folded in, see gemm_f16x3).
+    {
         const size_t col_blocks = (mn / 4 + 255) / 256;
         size_t slabs = cap / col_blocks;
         if (slabs < 1) slabs = 1;
@@ -1797,14 +1746,40 @@ static int prep16_operand(sl_ctx* ctx, const float* src, size_t mn, size_t k, bo
         int rc = sl_ws_reserve(ctx, (colsum_acc ? 2 : 1) * slabs * mn * sizeof(float), &partial);
         if (rc != SL_OK) return rc;
         float* psum = colsum_acc ? (float*)partial + slabs * mn : nullptr;
-        SL_LAUNCH(ctx, prep16_colmax_kernel, dim3((unsigned)col_blocks, (unsigned)slabs, 1), 256, 0, k, mn, rows_per_slab, src, (float*)partial, psum);
+        SL_LAUNCH(ctx, prep16_colmax_kernel, dim3((unsigned)col_blocks, (unsigned)slabs, 1), 256, 0, k, mn, rows_per_slab, src, (float*)partial, psum, row_factor);
         SL_LAUNCH(ctx, prep16_colscale_kernel, (unsigned)((mn + 31) / 32), dim3(32, 8, 1), 0, mn, (int)slabs, (const float*)partial, scale, scale_inv,
                   (const float*)psum, colsum_acc);
-        if (ctx->plane_scope) ctx->cols_split_done.push_back(src);
     }
     const size_t total = k * (mn / 4);
     size_t blocks = (total + 255) / 256;
-    SL_LAUNCH(ctx, prep16_cols_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, k, mn, src, use_scale, hi, lo);
+    SL_LAUNCH(ctx, prep16_cols_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, k, mn, src, (const float*)scale, hi, lo, row_factor);
+    return SL_OK;
+}
+
+// Row-scaled fp16 planes of a K-contiguous operand, kept for the rest of the scope (slots handed out in call order, grow-only)
+static sl_ctx::RowPlanes* rowplanes_find(sl_ctx* ctx, const void* src, size_t rows, size_t cols) {
+    for (auto& e : ctx->rowplane_cache)
+        if (e.valid && e.src == src && e.rows == rows && e.cols == cols) return &e;
+    return nullptr;
+}
+static int rowplanes_new(sl_ctx* ctx, const void* src, size_t rows, size_t cols, sl_ctx::RowPlanes** out) {
+    if (ctx->rowplane_cursor >= ctx->rowplane_cache.size())
+        ctx->rowplane_cache.push_back(sl_ctx::RowPlanes{nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0, false});
+    sl_ctx::RowPlanes& e = ctx->rowplane_cache[ctx->rowplane_cursor++];
+    const size_t bytes = (rows * cols * 2 + 255) & ~size_t(255);
+    if (e.cap_bytes < bytes || e.cap_rows < rows) {
+        SL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (e.hi) cudaFree(e.hi);
+        if (e.lo) cudaFree(e.lo);
+        if (e.inv) cudaFree(e.inv);
+        e.hi = e.lo = nullptr; e.inv = nullptr; e.cap_bytes = e.cap_rows = 0;
+        SL_CUDA(ctx, cudaMalloc(&e.hi, bytes));
+        SL_CUDA(ctx, cudaMalloc(&e.lo, bytes));
+        SL_CUDA(ctx, cudaMalloc((void**)&e.inv, rows * sizeof(float)));
+        e.cap_bytes = bytes; e.cap_rows = rows;
+    }
+    e.src = src; e.rows = rows; e.cols = cols; e.valid = true;
+    *out = &e;
     return SL_OK;
 }
 
@@ -1829,14 +1804,51 @@ static int gemm_f16x3(sl_ctx* ctx, int trans_a, int trans_b, size_t m, size_t n,
     float* b_sc = (float*)((char*)a_inv + sm);
     float* b_inv = (float*)((char*)b_sc + sn);
     const float *a_inv_use = nullptr, *b_inv_use = nullptr;
-    if ((rc = prep16_operand(ctx, a, m, k, a_kc, a_hi, a_lo, a_sc, a_inv, &a_inv_use, nullptr)) != SL_OK) return rc;
-    if ((rc = prep16_operand(ctx, b, n, k, b_kc, b_hi, b_lo, b_sc, b_inv, &b_inv_use, b_kc ? nullptr : b_colsum_acc)) != SL_OK) return rc;
+    // Inside a scope a K-contiguous operand's row-scaled planes are kept (and found again): the forward gemm's split of an
+    // activation [batch x width] serves the weight-gradient gemm of the same step, which contracts over the batch and reads the very
+    // same planes as its MN-major operand.  Their scaling is per ROW (= per k of that product), so it is undone inside the
+    // contraction: the OTHER operand is split as other[k][.] * (1 / s_k) — one exact power-of-two factor per row folded into its own
+    // column split — and the reused operand contributes no epilogue scale.  (Before: every activation was split twice per step,
+    // once per row and once per column: 4 of the 7 big operand passes of the MLP step were second splits.)
+    sl_ctx::RowPlanes *ra = nullptr, *rb = nullptr;
+    const bool scope = ctx->plane_scope && !env_int("SLICED_GEMM_NO_ROWPLANE_REUSE", 0);
+    if (scope && !a_kc && !b_kc) {
+        ra = rowplanes_find(ctx, a, k, m);
+        if (!ra) rb = rowplanes_find(ctx, b, k, n);
+    }
+    auto kmajor = [&](const float* src, size_t mn, __half*& hi, __half*& lo, float* inv_scratch, float* sc_scratch, const float** inv_use) -> int {
+        if (!scope) return prep16_operand(ctx, src, mn, k, true, hi, lo, sc_scratch, inv_scratch, inv_use, nullptr);
+        sl_ctx::RowPlanes* e = rowplanes_find(ctx, src, mn, k);
+        if (!e) {
+            int r = rowplanes_new(ctx, src, mn, k, &e);
+            if (r != SL_OK) return r;
+            const float* dummy = nullptr;
+            if ((r = prep16_operand(ctx, src, mn, k, true, (__half*)e->hi, (__half*)e->lo, sc_scratch, e->inv, &dummy, nullptr)) != SL_OK) return r;
+        }
+        hi = (__half*)e->hi; lo = (__half*)e->lo; *inv_use = e->inv;
+        return SL_OK;
+    };
+    if (ra) {          // A's planes exist (row-scaled over k): B is split with A's inverse row scales folded in
+        a_hi = (__half*)ra->hi; a_lo = (__half*)ra->lo; a_inv_use = nullptr;
+        if ((rc = prep16_operand(ctx, b, n, k, false, b_hi, b_lo, b_sc, b_inv, &b_inv_use, b_colsum_acc, ra->inv)) != SL_OK) return rc;
+    } else if (rb) {   // the mirror image
+        b_hi = (__half*)rb->hi; b_lo = (__half*)rb->lo; b_inv_use = nullptr;
+        if ((rc = prep16_operand(ctx, a, m, k, false, a_hi, a_lo, a_sc, a_inv, &a_inv_use, nullptr, rb->inv)) != SL_OK) return rc;
+        if (b_colsum_acc) {   // (the bias gradient normally rides B's column-maxima pass, which did not run)
+            if ((rc = sl_add_row_mut_grad(ctx, SL_F32, k, n, b_colsum_acc, b)) != SL_OK) return rc;
+        }
+    } else {
+        if (a_kc) { if ((rc = kmajor(a, m, a_hi, a_lo, a_inv, a_sc, &a_inv_use)) != SL_OK) return rc; }
+        else if ((rc = prep16_operand(ctx, a, m, k, false, a_hi, a_lo, a_sc, a_inv, &a_inv_use, nullptr)) != SL_OK) return rc;
+        if (b_kc) { if ((rc = kmajor(b, n, b_hi, b_lo, b_inv, b_sc, &b_inv_use)) != SL_OK) return rc; }
+        else if ((rc = prep16_operand(ctx, b, n, k, false, b_hi, b_lo, b_sc, b_inv, &b_inv_use, b_colsum_acc)) != SL_OK) return rc;
+    }
     if (m_chunks > 1 && !a_kc && !epi.any() && m % ((size_t)256 * m_chunks) == 0 && sl_gemm_pick_cfg(ctx, m / m_chunks, n) == 4) {
         const size_t mc = m / m_chunks;
         for (int ci = 0; ci < m_chunks; ++ci) {
             const size_t m0 = (size_t)ci * mc;
             rc = sl_gemm_tc_planes(ctx, (int)mc, (int)n, (int)k, a_hi + m0, a_lo + m0, m, b_hi, b_lo, b_kc ? k : n, c + m0 * n, nullptr, accumulate, 0,
-                                   nullptr, nullptr, 1, b_kc ? 0 : 1, 1, a_inv_use + m0, b_inv_use);
+                                   nullptr, nullptr, 1, b_kc ? 0 : 1, 1, a_inv_use ? a_inv_use + m0 : nullptr, b_inv_use);
             if (rc != SL_OK) return rc;
             if (exchange_chunks && (rc = sl_allreduce_sum_async(ctx, SL_F32, c + m0 * n, mc * n)) != SL_OK) return rc;
         }
@@ -2108,10 +2120,9 @@ static int linear_bwd_params_impl(sl_ctx* ctx, int dtype, size_t m, size_t k, si
 int sl_gemm_scope_begin(sl_ctx* ctx) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     for (auto& e : ctx->plane_cache) e.valid = false;
-    for (auto& e : ctx->colscale_cache) e.valid = false;
     ctx->plane_cursor = 0;
-    ctx->colscale_cursor = 0;
-    ctx->cols_split_done.clear();
+    for (auto& e : ctx->rowplane_cache) e.valid = false;
+    ctx->rowplane_cursor = 0;
     ctx->plane_scope = true;
     return SL_OK;
 }
@@ -2119,8 +2130,7 @@ int sl_gemm_scope_begin(sl_ctx* ctx) {
 int sl_gemm_scope_end(sl_ctx* ctx) {
     SL_REQUIRE(ctx, ctx != nullptr, "ctx is NULL");
     for (auto& e : ctx->plane_cache) e.valid = false;
-    for (auto& e : ctx->colscale_cache) e.valid = false;
-    ctx->cols_split_done.clear();
+    for (auto& e : ctx->rowplane_cache) e.valid = false;
     ctx->plane_scope = false;
     return SL_OK;
 }

@@ -555,3 +555,59 @@ def test_linear_mask_bits_variants_are_bit_identical(m, k, n, mode, monkeypatch)
         S.capi.check(ctx.h, L.sl_linear_bwd_input_relu_bits(ctx.h, S.F32, m, n, p_out, dw2.ptr, dg.ptr, bits.ptr, gx2.ptr, md))
         assert np.array_equal(gx.numpy().view(np.uint32), gx2.numpy().view(np.uint32)), p_out
     ctx.close()
+
+
+def test_rowplane_reuse_inside_a_scope(monkeypatch):
+    """3xFP16 inside a gemm scope: the row-scaled planes a forward gemm x[M x I] * w leaves behind serve the weight-gradient gemm
+    x^T g of the same scope (which contracts over x's ROWS) — x is not split a second time; its row scales are folded, as exact
+    powers of two, into the split of g.  Checked: (1) fp32-class against fp64 like every other gemm; (2) close to the same product
+    computed outside any scope (per-column split of x); (3) sl_gemm_grad's mirror image (out_grad's planes reused as the B operand)
+    and the bias-gradient column sums of sl_linear_bwd_params; (4) scaling rows of x by powers of two and the same rows of g by the
+    inverse leaves the result BIT-identical (both factors disappear into the row scales)."""
+    import sliced_b200 as S
+    monkeypatch.delenv("SLICED_GEMM_TC_FORCE", raising=False)
+    monkeypatch.setenv("SLICED_GEMM_F16_STRICT", "1")
+    ctx = S.Context(0)
+    L = ctx.lib
+    M, I, Oo = 8192, 2048, 2048
+    rng = np.random.default_rng(77)
+    x, w, g = _rand32(rng, M * I, 0, 1), _rand32(rng, I * Oo, -0.05, 0.05), _rand32(rng, M * Oo, -1e-3, 1e-3)
+    x.reshape(M, I)[5] = 0                       # an all-zero row (scale 1)
+    x.reshape(M, I)[7] *= np.float32(2.0 ** -30)  # a row far below the others
+    dx, dw, dg = ctx.array(x), ctx.array(w), ctx.array(g)
+    X, G = x.reshape(M, I), g.reshape(M, Oo)
+    rows, cols = _sample_idx(rng, I, Oo)
+    plain = ctx.gemm_tn(I, Oo, M, dx, dg).numpy().reshape(I, Oo)                  # no scope: x split per column
+    ctx.gemm_scope_begin()
+    ctx.gemm(M, I, Oo, dx, dw)                                                    # forward: leaves x's row planes
+    n0 = ctx.launches
+    reused = ctx.gemm_tn(I, Oo, M, dx, dg).numpy().reshape(I, Oo)
+    assert ctx.launches - n0 <= 5, "x must not be split again (colmax + colscale + cols of g, the gemm, at most a fold)"
+    bg = ctx.zeros(Oo)
+    wg = ctx.empty(I * Oo)
+    S.capi.check(ctx.h, L.sl_linear_bwd_params(ctx.h, S.F32, M, I, Oo, dx.ptr, dg.ptr, wg.ptr, bg.ptr, -1))
+    S.capi.check(ctx.h, L.sl_gemm_scope_end(ctx.h))
+    for got, what in ((plain, "plain"), (reused, "reused")):
+        _check_sampled(got[np.ix_(rows, cols)], X[:, rows].T.astype(np.float64), G[:, cols].astype(np.float64), M, rows, cols, what=what)
+    scale = np.max(np.abs(plain))
+    assert np.max(np.abs(reused - plain)) <= 4 * M * 2.0 ** -24 * 1e-3, np.max(np.abs(reused - plain)) / scale
+    assert np.array_equal(wg.numpy().reshape(I, Oo), reused)
+    assert np.max(np.abs(bg.numpy() - G.astype(np.float64).sum(0))) <= 4 * M * 2.0 ** -24 * 1e-3
+    # mirror image: sl_gemm_grad splits out_grad per row for lhs_grad and reuses those planes as the B operand of rhs_grad
+    lg, rg = ctx.empty(M * I), ctx.empty(I * Oo)
+    ctx.gemm_grad(M, I, Oo, dx, dw, lg, rg, dg)
+    _check_sampled(rg.numpy().reshape(I, Oo)[np.ix_(rows, cols)], X[:, rows].T.astype(np.float64), G[:, cols].astype(np.float64), M, rows, cols,
+                   what="gemm_grad rhs_grad")
+    r3, c3 = _sample_idx(rng, M, I)
+    W = w.reshape(I, Oo)
+    t = G[r3].astype(np.float64) @ W[c3].astype(np.float64).T
+    assert np.max(np.abs(lg.numpy().reshape(M, I)[np.ix_(r3, c3)] - t)) <= 4 * Oo * 2.0 ** -24 * 0.05 * 1e-3 * 4
+    # power-of-two row scalings cancel exactly
+    p = np.exp2(rng.integers(-20, 21, M)).astype(np.float32)
+    dx2, dg2 = ctx.array((X * p[:, None]).ravel()), ctx.array((G / p[:, None]).ravel())
+    ctx.gemm_scope_begin()
+    ctx.gemm(M, I, Oo, dx2, dw)
+    reused2 = ctx.gemm_tn(I, Oo, M, dx2, dg2).numpy().reshape(I, Oo)
+    S.capi.check(ctx.h, L.sl_gemm_scope_end(ctx.h))
+    assert np.array_equal(reused2.view(np.uint32), reused.view(np.uint32))
+    ctx.close()
