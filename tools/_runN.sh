@@ -1,11 +1,10 @@
 # usage: _runN.sh N  (multi-GPU bench under an inner timeout)
 N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 240 $TR --master-port 29531 bench.py --gpus $N --steps 40 --warmup 5 > gpurun_out/r2l_bench_n$N.json 2> gpurun_out/r2l_bench_n$N.err
-tail -c 300 gpurun_out/r2l_bench_n$N.err
+timeout 240 $TR --master-port 29531 bench.py --gpus $N --steps 40 --warmup 5 > gpurun_out/r2p_bench_n$N.json 2> gpurun_out/r2p_bench_n$N.err
+tail -c 300 gpurun_out/r2p_bench_n$N.err
 python - <<P
 import json
-d=json.loads(open('gpurun_out/r2l_bench_n$N.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/r2p_bench_n$N.json').read().strip().splitlines()[-1])
 print('N=$N ms', d['ms_per_step'], 'value', d['value'], 'e2e ms', d['e2e']['ms_per_step'], d['clocks'], d['parity_check'].get('dp'), d['config'].get('host_numa_node'))
 P
-nvidia-smi topo -m 2>/dev/null | head -14
