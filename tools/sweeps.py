@@ -232,7 +232,42 @@ def run_chained(B: Bench, log2n=28, reps=5):
     res["speedup_fwd"] = round(res["unfused_fwd"]["ms"] / res["fused_fwd"]["ms"], 2)
     res["speedup_bwd"] = round(res["unfused_bwd"]["ms"] / res["fused_bwd"]["ms"], 2)
     B.release()
+    res["tape_n100"] = run_tape_overhead()
     return res
+
+
+def run_tape_overhead(n=100, iters=300):
+    """tape overhead at N = 100 (cf. tests/test_combination.rs:103-105): the same graph through the host tape
+    (5 forward ops + their 5 grad closures), wall clock per op, on the plain device (one launch per op) and on the fusing device (the
+    chain is recorded and runs as one forward + one backward launch)."""
+    from sliced_b200.host import CUDA
+    out = {}
+    xs, bs = np.full(n, 1.3, np.float32), np.full(n, 2.1, np.float32)
+    for name in ("plain", "fused"):
+        dev = CUDA(0, cached=True)
+        dev.set_fusion(name == "fused")
+        x, b = dev.buffer(xs), dev.buffer(bs)
+
+        def step():
+            dev.zero_grad()
+            o = dev.add(dev.mul(dev.square(x), x), dev.mul(dev.add(b, x), b))
+            o.backward()
+            return o
+        for _ in dev.range(5):
+            step()
+        dev.sync()
+        l0 = dev.launches
+        t0 = time.perf_counter()
+        for _ in dev.range(iters):    # `for _ in device.range(..)`: the Cached cursor rewinds every iteration
+            step()
+        dev.sync()
+        dt = time.perf_counter() - t0
+        out[name] = dict(us_per_graph=round(1e6 * dt / iters, 1), us_per_op=round(1e6 * dt / iters / 10, 2), launches_per_graph=round((dev.launches - l0) / iters, 1))
+        del x, b
+        dev.close()
+    out["n"] = n
+    out["ops_per_graph"] = 10
+    return out
 
 
 def run_sine_net(device_index=0, iters=300):
