@@ -209,6 +209,28 @@ def cpu_reference_rate(steps: int, warmup: int, sample_batch: int):
                        f"(the reference's slice loops are single-threaded)"), dt
 
 
+def cpu_sine_net_us(steps=300):
+    """examples/sine_net.rs at its shipped sizes on the CPU port: us per training step.  gemm = OpenBLAS sgemm on ONE thread (measured
+    here: 1.8 ms per step; 16 threads thrash on 1000 x 64 matrices: 47 ms; the naive loop: 6.9 ms), everything else the single-thread
+    oracle loops like the reference's."""
+    import oracle as O
+    O.use_openblas(1)
+    dims = [1, 64, 64, 1]
+    xs = (np.arange(1000) / 1000.0).astype(np.float32)
+    ys = np.sin(2.0 * xs * np.float32(np.pi)).astype(np.float32)
+    rng = np.random.default_rng(0)
+    W = [rng.uniform(-0.5, 0.5, dims[i] * dims[i + 1]).astype(np.float32) for i in range(3)]
+    B = [np.zeros(dims[i + 1], np.float32) for i in range(3)]
+    for _ in range(10):
+        O.mlp_step(1, dims, xs, ys, None, W, B, 1e-4)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.mlp_step(1, dims, xs, ys, None, W, B, 1e-4)
+    us = round(1e6 * (time.perf_counter() - t0) / steps, 1)
+    O.use_naive_gemm()
+    return us
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -513,6 +535,7 @@ def run_ours(args):
             line["sweeps"] = sweeps_out
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_rate(1, 0, args.cpu_sample)   # one full-batch step: ~15-20 s of host time
+            cb["sine_net_us_per_step"] = cpu_sine_net_us()      # the same CPU port beside sweeps.sine_net
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
         if parity is not None and not parity["ok"]:
