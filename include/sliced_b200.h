@@ -284,9 +284,12 @@ int sl_linear_bwd_params(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, c
 int sl_linear_bwd_params_exchange(sl_ctx* ctx, int dtype, size_t m, size_t k, size_t n, const void* lhs, const void* out_grad, void* w_grad,
                                   void* b_grad, int chunks, int mode);
 
-/* Operand-plane reuse scope for the tensor-core gemm.  Every f32 gemm first derives TF32 hi/lo planes from its operands; between
- * begin and end those planes are kept and reused by later gemms that read the SAME buffer (same pointer and size) — e.g. an
- * activation in its forward gemm and again in the weight-gradient gemm of the same training step.  Every entry point of this
+/* Operand-plane reuse scope for the tensor-core gemm.  Every f32 gemm first derives half-width hi/lo planes from its operands
+ * (fp16 planes scaled per row / column in the default 3xFP16 mode, tf32 planes in 3xTF32 mode); between begin and end those planes
+ * are kept and reused by later gemms that read the SAME buffer (same pointer and size) — e.g. an activation in its forward gemm and
+ * again in the weight-gradient gemm of the same training step (3xFP16: the row-scaled planes of the forward serve the gemm that
+ * contracts over the buffer's rows, with the row scales folded exactly into the other operand's split; results stay within the
+ * mode's stated tolerance but are not bit-identical to the same product computed outside a scope).  Every entry point of this
  * library that writes device memory (ops, sl_write, sl_copy, sl_clear, the all-reduce) drops the cached planes / scales of the
  * buffer it writes, so reuse is always coherent with library calls; only writes from OUTSIDE the library (another stream, another
  * library) to a buffer read by a gemm earlier in the scope are the caller's responsibility.  sl_gemm_grad opens an implicit scope
