@@ -1490,6 +1490,63 @@ __global__ void __launch_bounds__(256) splitk_fold_kernel(size_t total, size_t n
     }
 }
 
+// 128-bit variant (n % 4 == 0, 16-byte aligned pointers; with mask bits n % 32 == 0): a thread folds 4 consecutive elements; the 8
+// threads covering one mask word combine their 4-bit nibbles with three shuffles.  Same per-element arithmetic and order as above.
+__global__ void __launch_bounds__(256) splitk_fold_vec_kernel(size_t total4, size_t n, int splits, const float* __restrict__ partial, float* C, int accumulate,
+                                                              const float* __restrict__ bias, int relu, float* C2, const float* __restrict__ mask_src,
+                                                              const uint32_t* __restrict__ bits_in, uint32_t* bits_out) {
+    const size_t total = total4 * 4;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = q * 4;
+        const Pack<float> p0 = ld_stream(partial + i);
+        float v[4] = {p0.v[0], p0.v[1], p0.v[2], p0.v[3]};
+        for (int s = 1; s < splits; ++s) {
+            const Pack<float> ps = ld_stream(partial + (size_t)s * total + i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] += ps.v[e];
+        }
+        if (accumulate) {
+            const Pack<float> c = ld_pack(C + i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] += c.v[e];
+        }
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + i % n));
+            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        }
+        if (mask_src) {
+            const Pack<float> m = ld_stream(mask_src + i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = (m.v[e] >= 0.f ? 1.f : 0.f) * v[e];
+        }
+        if (bits_in) {
+            const uint32_t w = __ldg(bits_in + (i >> 5)) >> (i & 31);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = ((w >> e) & 1u ? 1.f : 0.f) * v[e];
+        }
+        if (bits_out) {   // (total4 % 8 == 0 because n % 32 == 0: the 8 threads of a word are all inside the loop together)
+            uint32_t w = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w |= (v[e] >= 0.f ? 1u : 0u) << e;
+            w <<= 4 * (threadIdx.x & 7);
+            const uint32_t grp = 0xFFu << (threadIdx.x & 24);   // the 8 lanes of this word (they enter and leave the loop together)
+            w |= __shfl_xor_sync(grp, w, 1);
+            w |= __shfl_xor_sync(grp, w, 2);
+            w |= __shfl_xor_sync(grp, w, 4);
+            if ((threadIdx.x & 7) == 0) bits_out[i >> 5] = w;
+        }
+        Pack<float> o, o2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (relu) v[e] = (v[e] >= 0.f ? 1.f : 0.f) * v[e];
+            o.v[e] = v[e];
+            o2.v[e] = (v[e] >= 0.f ? 1.f : 0.f) * v[e];
+        }
+        st_pack(C + i, o);
+        if (C2) st_pack(C2 + i, o2);
+    }
+}
+
 // Runs the tensor-core kernel on prepared K-major planes: C[M x N] (=|+=) A[M x K] * B[N x K]^T (+ bias, relu).
 // a_lo / b_lo are NULL in TF32 mode.  lda / ldb in floats, multiples of 4, planes 16-byte aligned.
 // kind 1: the planes are fp16 (3xFP16 mode, 2-CTA kernel only; lda / ldb in halves, multiples of 8) and row_scale [M] / col_scale [N]
@@ -1565,7 +1622,9 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
             const long units = tiles * sp;
             const long waves = (units + pairs - 1) / pairs;
             const int kbs = (num_kb + sp - 1) / sp;
-            const double fold_us = sp > 1 ? 2.0 * sp * (double)M * N * 4.0 / 4.0e12 * 1e6 + 4.0 : 0.0;   // measured: 67 us for 2 x 64 MB partials
+            // (a deliberately pessimistic fold cost: with the vectorised fold kernel a 2-way split at K = 8192 — the weight gradient
+            // of an 8-GPU run — measures the same as no split, 3.28 vs 3.29 ms per step, so the variant with fewer launches is kept)
+            const double fold_us = sp > 1 ? 2.0 * sp * (double)M * N * 4.0 / 4.0e12 * 1e6 + 4.0 : 0.0;
             return (double)waves * kbs * us_wave_kb + fold_us;
         };
         if (eff(tiles) < 0.92)
@@ -1598,6 +1657,12 @@ int sl_gemm_tc_planes(sl_ctx* ctx, int M, int N, int K, const void* a_hi, const 
         const size_t total = (size_t)M * N;
         const size_t cap = (size_t)ctx->num_sms * 8;
         size_t blocks = (total + 255) / 256;
+        if (p.c_vec_ok && total % 32 == 0 && !env_int("SLICED_GEMM_FOLD_SCALAR", 0)) {
+            blocks = (total / 4 + 255) / 256;
+            SL_LAUNCH(ctx, splitk_fold_vec_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, total / 4, (size_t)N, best, (const float*)q.C, final_c,
+                      p.accumulate, p.bias, p.relu, p.C2, p.mask_src, p.bits_in, p.bits_out);
+            return SL_OK;
+        }
         SL_LAUNCH(ctx, splitk_fold_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, total, (size_t)N, best, (const float*)q.C, final_c, p.accumulate,
                   p.bias, p.relu, p.C2, p.mask_src, p.bits_in, p.bits_out);
         return SL_OK;
