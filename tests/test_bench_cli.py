@@ -28,3 +28,28 @@ def test_reference_arm_other_ranks_exit_quietly():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--cpu-sample", "256"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert p.returncode == 0 and not [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_numa_binding_is_a_noop_without_topology():
+    """bench.bind_to_gpu_numa_node must never fail a run: no GPU / no sysfs topology -> None and the affinity is left alone"""
+    sys.path.insert(0, ROOT)
+    import bench
+    before = os.sched_getaffinity(0)
+    assert bench.bind_to_gpu_numa_node(0) is None or isinstance(bench.bind_to_gpu_numa_node(0), int)
+    assert os.sched_getaffinity(0) <= before
+
+
+def test_sweep_tables_regenerate_from_the_committed_bench_line(tmp_path):
+    """profiles/r2_opbench_*.txt are generated from the `sweeps` key of a bench line (tools/sweeps.py --from-bench-json): the committed
+    N=1 line must carry all four configs and the writer must reproduce the committed op table."""
+    sys.path.insert(0, ROOT)
+    from tools import sweeps
+    line = [ln for ln in open(os.path.join(ROOT, "profiles", "r2p_bench_n1.json")).read().splitlines() if ln.startswith("{")][-1]
+    sw = json.loads(line)["sweeps"]
+    for key in ("gemm", "ops", "chained", "sine_net"):
+        assert key in sw, key
+    assert {r["n"] for r in sw["gemm"]["rows"]} == {512, 1024, 2048, 4096, 8192, 16384}
+    assert {r["mode"] for r in sw["gemm"]["rows"]} == {"3xf16", "3xtf32", "tf32"} and {r["layout"] for r in sw["gemm"]["rows"]} == {"NN", "NT", "TN"}
+    assert len(sw["ops"]["ops"]) >= 34 and "one_launch" in sw["sine_net"]
+    sweeps.write_tables(sw, str(tmp_path / "x"))
+    assert open(tmp_path / "x_opbench_ops_16384.txt").read() == open(os.path.join(ROOT, "profiles", "r2_opbench_ops_16384.txt")).read()
