@@ -40,6 +40,9 @@ struct sl_ctx {
     struct RowPlanes { const void* src; size_t rows, cols; void* hi; void* lo; float* inv; size_t cap_bytes, cap_rows; bool valid; };
     std::vector<RowPlanes> rowplane_cache;
     size_t rowplane_cursor = 0;
+    // sl_mlp_small_step: function attributes are per device, so their one-time setup is remembered per context
+    bool mlp_small_attr = false;
+    int mlp_small_can16 = -1;   // -1 unknown | 0 | 1: a 16-CTA cluster of the kernel can be placed on this device
     // second stream for host->device prefetch (sl_write_prefetch), created lazily
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_done = nullptr, compute_done = nullptr;

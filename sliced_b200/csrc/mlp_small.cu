@@ -403,7 +403,7 @@ size_t plan(SmallMlpArgs& a, int n_layers, const size_t* dims, size_t batch, int
 // 16 CTAs (a non-portable cluster size: one whole GPC) when there are enough samples to feed them and the device can place such a
 // cluster with this much shared memory; else the portable 8
 int pick_cluster(sl_ctx* ctx, int n_layers, const size_t* dims, size_t batch) {
-    static int can16 = -1;   // per process (one device per process)
+    int& can16 = ctx->mlp_small_can16;
     if (batch < 256) return 8;
     SmallMlpArgs a{};
     const size_t bytes = plan(a, n_layers, dims, batch, 16);
@@ -425,7 +425,6 @@ int pick_cluster(sl_ctx* ctx, int n_layers, const size_t* dims, size_t batch) {
         }
         cudaGetLastError();
     }
-    (void)ctx;
     return can16 == 1 ? 16 : 8;
 }
 
@@ -443,10 +442,9 @@ extern "C" int sl_mlp_small_step(sl_ctx* ctx, int dtype, int n_layers, const siz
     SL_REQUIRE(ctx, dtype == SL_F32, "f32 only");
     SL_REQUIRE(ctx, dims && seg_off && x && y && params && grads && loss_sum_dev, "null argument");
     SL_REQUIRE(ctx, sl_aligned16(params) && sl_aligned16(grads), "params / grads must be 16-byte aligned");
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->mlp_small_attr) {
         SL_CUDA(ctx, cudaFuncSetAttribute(mlp_small_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        ctx->mlp_small_attr = true;
     }
     SmallMlpArgs a{};
     if (!plan(a, n_layers, dims, batch, 8))
